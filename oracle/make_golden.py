@@ -1,0 +1,220 @@
+"""oracle/make_golden.py -- TEST INFRASTRUCTURE ONLY.  Run in the build container:
+
+    python -m oracle.make_golden
+
+1. imports the REAL reference (oracle/ref_import.py) and runs it on CPU fp32 on seeded synthetic inputs;
+2. asserts oracle/geodiff_oracle.py reproduces it (bit-exact for geometry, 1e-5 for float math);
+3. writes tests/golden/*.npz (small arrays in full, large arrays as sha256 + samples).
+
+/root/reference does not travel to the GPU box: tests read only the committed .npz files.
+"""
+import hashlib
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import geodiff_oracle as O
+from geodiffuser_b200 import synth
+from .ref_import import load_reference
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def check(name, a, b, tol=0.0):
+    a, b = np.asarray(a), np.asarray(b)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    if tol == 0.0:
+        bad = int((a != b).sum())
+        print(f"  [{'OK' if bad == 0 else 'DIFF'}] {name}: bit-exact mismatches = {bad}/{a.size}"
+              + ("" if bad == 0 else f" max|d|={np.abs(a.astype(np.float64) - b.astype(np.float64)).max():.3e}"))
+        return bad
+    err = float(np.abs(a.astype(np.float64) - b.astype(np.float64)).max() / (np.abs(b).max() + 1e-12))
+    print(f"  [{'OK' if err <= tol else 'DIFF'}] {name}: rel-max err = {err:.3e} (tol {tol})")
+    assert err <= tol, name
+    return err
+
+
+def geometry_case(R, name, cfg):
+    print(f"== geometry case {name}")
+    image, depth, mask, T = synth.edit_inputs(cfg)
+    (pimg, valid, dproj, coords_ref, pmask_ref), d_used, mask_t = R.get_transform_coordinates_cpu(
+        image / 255.0, depth.copy(), mask.copy(), T, return_mesh=True)
+    coords_ref = coords_ref[0].numpy()
+    g = O.corr_build(depth.copy(), mask.copy(), T)
+    rec = {}
+    rec["coords_mismatch_vs_reference"] = check("coords@512 oracle vs reference", g["coords"], coords_ref)
+    ulp = np.abs(g["coords"].view(np.int32).astype(np.int64) - coords_ref.view(np.int32).astype(np.int64)).max()
+    print(f"     max ulp distance {ulp}")
+    rec["coords_max_ulp_vs_reference"] = int(ulp)
+    rec["coords512_sha"] = sha(g["coords"])
+    rec["coords512_ref_sha"] = sha(coords_ref)
+    rec["centre"] = g["centre"]
+    # how far the canonical (double-accumulated) centroid moves the integer artefact vs the reference run here
+    i_can, _, _ = O.splat_index(O.resize_coords(g["coords"], 64)[None])
+    i_ref, _, _ = O.splat_index(O.resize_coords(coords_ref, 64)[None])
+    rec["idx64_mismatch_canonical_vs_reference_coords"] = int((i_can != i_ref).sum())
+    print(f"     idx@64 entries differing (canonical centroid vs reference fp32 mean): {(i_can != i_ref).sum()}/{i_can.size}")
+    rec["Tc"] = g["Tc"]
+    # amodal mesh mask (A2) + erode (editor.py:633)
+    mm = O.mesh_mask(g["coords"], g["mask"])
+    check("mesh mask oracle vs shimmed reference", mm, pmask_ref[0, 0].numpy())
+    amodal = O.erode3(mm)
+    check("amodal erode", amodal, R.gt.torch_erode(pmask_ref)[0, 0].numpy())
+    rec["amodal512_sha"] = sha(amodal)
+    rec["amodal512_sum"] = float(amodal.sum())
+    # mask warp at 512 (editor.py:147-149)
+    tc = torch.from_numpy(coords_ref)[None]
+    image_mask2 = torch.from_numpy(mask.astype(np.float32))[None].tile(2, 1, 1)
+    t_coords_m = R.gt.reshape_transform_coords(tc, in_mat_shape=image_mask2.shape).tile(2, 1, 1, 1)
+    mnw_ref = R.gt.binarize_tensor(R.wu.warp_grid_edit(image_mask2[:, None], t_coords_m))
+    idx512, _, d2 = O.splat_index(np.broadcast_to(coords_ref[None], (1, 512, 512, 3)))
+    mnw = O.binarize(O.splat_composite(mask.astype(np.float32)[None, None], idx512, d2))[0, 0]
+    check("mask_new_warped@512", mnw, mnw_ref[0, 0].numpy())
+    rec["idx512_sha"] = sha(idx512)
+    rec["mask_new_warped512_sha"] = sha(mnw)
+    rec["mask_new_warped512_sum"] = float(mnw.sum())
+    for S in (64, 32, 16, 8):
+        cS_ref = R.gt.reshape_transform_coords(tc, in_mat_shape=(1, 1, S, S))[0].numpy()
+        cS = O.resize_coords(coords_ref, S)
+        check(f"coords@{S} resize", cS, cS_ref)
+        idx, zb, dd = O.splat_index(cS[None])
+        rec[f"coords{S}"] = cS
+        rec[f"idx{S}"] = idx[0]
+        rec[f"dist2_{S}"] = dd[0]
+        # masks (attention_processors.py:338-360) through the reference's own function
+        qd = torch.zeros(1, 1, S * S, 4)
+        qeb = torch.zeros(1, 4, S, S)
+        _, _, m1, m2, m3, m4, m5, m6, tcq = R.ap.process_and_cache_masks(
+            {}, S, image_mask2.clone(), mnw_ref.clone(), torch.from_numpy(amodal)[None, None], tc, qd, qeb)
+        mk = O.build_masks(mask, mnw, amodal, S)
+        for nm, ref_m in (("mask_new_warped", m1), ("mask_warp", m2), ("amodal_mask", m3), ("mask_intersection", m4),
+                          ("mask_1_empty", m5), ("mask_wo_edit", m6)):
+            check(f"{nm}@{S}", mk[nm], ref_m[0, 0].numpy())
+            rec[f"{nm}{S}"] = mk[nm]
+        check(f"t_coords_q@{S}", cS, tcq[0].numpy())
+        # feature warp through the reference's splatter vs oracle
+        rs = np.random.RandomState(7 + S)
+        feat = rs.randn(2, 3, S, S).astype(np.float32)
+        w_ref = R.wu.warp_grid_edit(torch.from_numpy(feat), torch.from_numpy(cS)[None].tile(2, 1, 1, 1)).float().numpy()
+        w_or = O.warp_grid_edit(feat, np.broadcast_to(cS[None], (2, S, S, 3)))
+        # alpha uses torch's `.pow(0.5)` (Sleef, <=1 ulp, not correctly rounded) in the reference and IEEE sqrt
+        # in the oracle: outputs may differ by one fp16 ulp in isolated elements (float quantity, tolerance-checked)
+        check(f"feature warp@{S}", w_or, w_ref, 1e-3)
+        rec[f"warp_feat{S}_n_diff_vs_reference"] = int((w_or != w_ref).sum())
+        rec[f"warp_feat{S}"] = w_or
+    np.savez_compressed(os.path.join(OUT, f"geometry_{name}.npz"), **rec)
+    return dict(coords=coords_ref, mask=mask, mnw=mnw_ref, amodal=amodal)
+
+
+def make_ref_controller(R, kind, mask, geo, num_steps=50, obj_edit_step=0.9):
+    prompts = ["", ""]
+    cls = R.ap.AttentionGeometryEdit if kind == "edit" else R.ap.AttentionGeometryRemover
+    c = cls(prompts, num_steps, cross_replace_steps={"default_": 0.95}, self_replace_steps=0.95, image_mask=mask.astype(np.float32),
+            empty_scale=0.0, use_all=False, obj_edit_step=obj_edit_step, tokenizer=None, device="cpu", mode="bilinear")
+    c.num_att_layers = 32
+    c.amodal_mask = torch.from_numpy(geo["amodal"])[None, None]
+    c.mask_new_warped = geo["mnw"].clone()
+    return c
+
+
+def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_step=0):
+    print(f"== attention case {name}")
+    c = make_ref_controller(R, kind, geo["mask"], geo)
+    c.cur_step = cur_step
+    B = 4 if use_cfg else 2
+    c.use_cfg = use_cfg
+    c.coords_base, c.coords_edit = ((2, 3), (3, 4)) if use_cfg else ((0, 1), (1, 2))
+    q, k, v = synth.qkv(seed, B, H, S * S, 77 if is_cross else S * S, d)
+    q, k, v = (torch.from_numpy(a).requires_grad_(not use_cfg) for a in (q, k, v))
+    scale = d ** -0.5
+    tc = torch.from_numpy(geo["coords"])[None]
+    with torch.set_grad_enabled(not use_cfg):
+        out_ref = c(q, k, v, is_cross, "down", transform_coords=tc, scale=scale, mask=None)
+    rec = dict(out=out_ref.detach().numpy())
+    # oracle restatement
+    q2, k2, v2 = (a.detach().clone().requires_grad_(not use_cfg) for a in (q, k, v))
+    blend = cur_step < int(50 * 0.9)
+    with torch.set_grad_enabled(not use_cfg):
+        if kind == "edit":
+            masks = O.build_masks(geo["mask"], geo["mnw"][0, 0].numpy(), geo["amodal"], S)
+            res = O.edit_layer(q2, k2, v2, is_cross, scale, H, c.coords_base, c.coords_edit, masks,
+                               O.resize_coords(geo["coords"], S), use_cfg, blend)
+        else:
+            res = O.remover_layer(q2, k2, v2, is_cross, scale, H, c.coords_base, c.coords_edit,
+                                  O.dilate(geo["mask"], 5), use_cfg, blend)
+    check("out", res["out"].detach().numpy(), rec["out"], 2e-5)
+    if not use_cfg and S >= 32:
+        loss_ref = c.loss
+        gq, gk = torch.autograd.grad(loss_ref + 0.37 * out_ref.sum(), [q, k], allow_unused=True)
+        g2q, g2k = torch.autograd.grad(res["loss"] + 0.37 * res["out"].sum(), [q2, k2], allow_unused=True)
+        check("loss", res["loss"].item(), loss_ref.item(), 2e-5)
+        check("dq", g2q.numpy(), gq.numpy(), 1e-4)
+        rec["loss"] = np.float64(loss_ref.item())
+        rec["dq"] = gq.numpy()
+        if gk is not None:
+            check("dk", g2k.numpy(), gk.numpy(), 1e-4)
+            rec["dk"] = gk.numpy()
+        for key, val in c.loss_log_dict["cross" if is_cross else "self"].items():
+            rec["term_" + key] = np.float64(float(val))
+            check("term " + key, float(res["terms"][key]), float(val), 5e-5)
+        if kind == "edit":
+            rec["term_amodal"] = np.float64(float(res["terms"]["amodal"]))
+    rec["meta"] = np.array([S, H, d, int(is_cross), int(use_cfg), seed, cur_step])
+    np.savez_compressed(os.path.join(OUT, f"attn_{name}.npz"), **rec)
+
+
+def elementwise_case(R):
+    print("== elementwise case")
+    rs = np.random.RandomState(11)
+    lat = torch.from_numpy(rs.randn(2, 4, 64, 64).astype(np.float32))
+    ctx = torch.from_numpy(rs.randn(2, 77, 768).astype(np.float32))
+    mask512 = (rs.rand(512, 512) > 0.7).astype(np.float32)
+    lat_r = lat.clone().requires_grad_(True)
+    ctx_r = ctx.clone().requires_grad_(True)
+    w1 = torch.from_numpy(rs.randn(2, 4, 64, 64).astype(np.float32))
+    w2 = torch.from_numpy(rs.randn(2, 77, 768).astype(np.float32))
+    loss = (lat_r * w1).sum() + (ctx_r * w2).sum() * 0.5
+    nl_ref, nc_ref = R.opt._update_latent(lat_r, loss, 0.3, torch.from_numpy(mask512), ctx_r)
+    g1 = w1.clone()
+    g1[1, 0, 0, 0] = float("nan")  # nan_to_num path exercised through the oracle only
+    nl, nc = O.update_latent(lat, w1, 0.3, mask512, ctx, 0.5 * w2)
+    check("update_latent", nl.numpy(), nl_ref.detach().numpy(), 1e-6)
+    check("update_context", nc.numpy(), nc_ref.detach().numpy(), 1e-6)
+    al = O.ddim_alphas()
+    ts = O.ddim_timesteps()
+    assert ts[0] == 980 and ts[-1] == 0
+    eps = torch.from_numpy(rs.randn(2, 4, 64, 64).astype(np.float32))
+    np.savez_compressed(os.path.join(OUT, "elementwise.npz"), lat=lat.numpy(), ctx=ctx.numpy(), mask512=mask512, w1=w1.numpy(),
+                        w2=w2.numpy(), new_lat=nl_ref.detach().numpy(), new_ctx=nc_ref.detach().numpy(), eps=eps.numpy(),
+                        ddim_980=O.ddim_step(lat, eps, 980, al).numpy(), ddim_0=O.ddim_step(lat, eps, 0, al).numpy(),
+                        alphas=al.numpy())
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_grad_enabled(True)
+    R = load_reference()
+    geos = {}
+    for name in ("translate2d", "rotate3d", "remove"):
+        geos[name] = geometry_case(R, name, name)
+    attention_case(R, "edit_self_S32_opt", geos["translate2d"], "edit", 32, 2, 16, False, False, 101)
+    attention_case(R, "edit_self_S64_opt", geos["rotate3d"], "edit", 64, 1, 8, False, False, 102)
+    attention_case(R, "edit_cross_S32_opt", geos["translate2d"], "edit", 32, 2, 16, True, False, 103)
+    attention_case(R, "edit_self_S32_cfg", geos["rotate3d"], "edit", 32, 2, 16, False, True, 104)
+    attention_case(R, "edit_self_S16_cfg_late", geos["translate2d"], "edit", 16, 2, 32, False, True, 105, cur_step=46)
+    attention_case(R, "edit_cross_S16_cfg", geos["translate2d"], "edit", 16, 2, 32, True, True, 106)
+    attention_case(R, "remove_self_S32_opt", geos["remove"], "remove", 32, 2, 16, False, False, 107)
+    attention_case(R, "remove_cross_S32_opt", geos["remove"], "remove", 32, 2, 16, True, False, 108)
+    attention_case(R, "remove_self_S32_cfg_late", geos["remove"], "remove", 32, 2, 16, False, True, 109, cur_step=46)
+    elementwise_case(R)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
