@@ -1,0 +1,105 @@
+"""ctypes binding of the C-ABI CUDA library (include/geodiffuser_b200.h).
+
+There is NO fallback: if libgeodiffuser_b200.so is missing or a call returns a non-zero status this module raises.
+PyTorch is used by the callers only for device memory, streams and autograd plumbing.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgeodiffuser_b200.so")
+
+P, I, F, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_long
+
+# name -> argument ctypes (every entry point returns int status); mirrors include/geodiffuser_b200.h
+SIGNATURES = {
+    "gd_corr_pixel2cam": [P, P, I, I, P, P, P, P],
+    "gd_corr_project": [P, I, I, P, P, P, P],
+    "gd_resize_bilinear": [P, I, I, I, I, P, I, I, P],
+    "gd_masks_build": [P, P, P, I, I, P, P],
+    "gd_splat_index": [P, I, I, F, I, P, P, P, P],
+    "gd_splat_composite": [P, I, I, P, P, I, I, I, I, I, F, F, P, I, P, I, P],
+    "gd_mesh_mask": [P, P, I, I, F, P, P],
+    "gd_morph": [P, I, I, I, I, I, P, P],
+    "gd_attn_fwd_generic": [P, P, P, P, P, I, I, I, I, I, F, P],
+    "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, I, I, I, I, P, P, P],
+    "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P],
+    "gd_cast_f32_to_bf16": [P, P, L, P],
+    "gd_attn_probs": [P, P, P, P, I, I, I, I, I, F, P, I, P],
+    "gd_corr_max_partial": [P, P, I, I, I, I, I, P, P, P, P],
+    "gd_attn_l1_losses": [P, P, P, P, P, P, P, F, F, F, F, F, I, I, I, P, P, I, P],
+    "gd_removal_finalize": [P, I, I, I, I, P, P, P, F, P, I, I, I, P, P, P, P, P, P],
+    "gd_loss_reduce": [P, I, P, I, P, P, F, P, P, P],
+    "gd_amodal_knn": [P, I, P, P, P, P],
+    "gd_amodal_target": [P, P, P, P, P, I, I, I, P, P, P],
+    "gd_blend_rows": [P, P, P, P, I, I, I, P, I, P],
+    "gd_ddim_step": [P, P, P, I, F, F, F, F, F, L, P, P, P],
+    "gd_latent_update": [P, P, P, I, F, L, P, P],
+    "gd_norm_rescale": [P, L, F, P, P],
+    "gd_latent_blend": [P, P, P, I, I, L, P, P],
+}
+
+_LIB = None
+HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
+LAUNCHES = 0  # kernels-launching C-ABI calls made by this process (bench.py reports it)
+
+
+class GeoDiffuserB200Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Loads the shared library once.  Raises if it has not been built (python -c 'import __graft_entry__ as g; g.build()')."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise GeoDiffuserB200Error(
+                f"{LIB_PATH} not found: the sm_100a CUDA extension is not built and there is no CPU fallback. "
+                "Run `sh geodiffuser_b200/csrc/build.sh`.")
+        L_ = ctypes.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(L_, name)  # AttributeError here == header / library mismatch
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        L_.gd_last_error.restype = ctypes.c_char_p
+        L_.gd_version.restype = ctypes.c_int
+        _LIB = L_
+    return _LIB
+
+
+def call(name, *args):
+    global LAUNCHES
+    L_ = lib()
+    rc = getattr(L_, name)(*args)
+    LAUNCHES += 1
+    if rc != 0:
+        raise GeoDiffuserB200Error(f"{name} failed with status {rc}: {L_.gd_last_error().decode()}")
+
+
+def ptr(t):
+    """device pointer of a contiguous CUDA tensor (None -> NULL)"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GeoDiffuserB200Error("expected a CUDA tensor: geodiffuser_b200 has no CPU path")
+    if not t.is_contiguous():
+        raise GeoDiffuserB200Error("expected a contiguous tensor")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def host_f32(values):
+    """host float array for the few entry points that take small host-side matrices"""
+    arr = (ctypes.c_float * len(values))(*[float(v) for v in values])
+    return arr
+
+
+def ptr_array(tensors):
+    """host array of device pointers"""
+    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    return arr
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,25 @@
+#!/bin/sh
+# Builds geodiffuser_b200/libgeodiffuser_b200.so for sm_100a, in-tree (the .so travels to the GPU box with the snapshot).
+set -e
+cd "$(dirname "$0")"
+OUT=../libgeodiffuser_b200.so
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $ARCH"
+mkdir -p _obj
+pids=""
+# geometry.cu: bit-exact integer artefacts behind an fp32 pipeline -> no FMA contraction
+$NVCC $COMMON -fmad=false -c geometry.cu -o _obj/geometry.o 2> _obj/geometry.log & pids="$pids $!"
+for f in attention_mma corr_gemm losses elementwise attention_sm100; do
+    if [ -f $f.cu ]; then
+        $NVCC $COMMON -c $f.cu -o _obj/$f.o 2> _obj/$f.log & pids="$pids $!"
+    fi
+done
+fail=0
+for p in $pids; do wait $p || fail=1; done
+if [ $fail -ne 0 ]; then
+    grep -h -E "error|Error" -A3 _obj/*.log || cat _obj/*.log
+    exit 1
+fi
+$NVCC $ARCH -shared -o $OUT _obj/*.o -lcudart -lcuda
+echo "built $(cd .. && pwd)/libgeodiffuser_b200.so"

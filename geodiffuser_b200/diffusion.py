@@ -1,0 +1,96 @@
+"""DDIM scheduler + `diffusion_step` of the edit loop, mirroring /root/reference/GeoDiffuser/utils/diffusion.py:40-59 and the
+diffusers-0.25 DDIMScheduler configuration the reference builds at diffusion.py:110 (scaled_linear betas 0.00085..0.012,
+clip_sample=False, set_alpha_to_one=False, leading timestep spacing, eta = 0).  The elementwise update (CFG combine + x_{t-1})
+is one CUDA launch (csrc/elementwise.cu) instead of ~12 tiny torch kernels."""
+import numpy as np
+import torch
+
+from ._lib import call, ptr, stream
+
+AUTOCAST_DTYPE = torch.bfloat16  # the reference autocasts to fp16 (diffusion.py:39); BASELINE.json names BF16 for this build
+
+
+class DDIMScheduler:
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
+        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = self.alphas_cumprod[0]  # set_alpha_to_one=False
+        self.num_train_timesteps = num_train_timesteps
+        self.num_inference_steps = None
+        self.timesteps = None
+
+    def set_timesteps(self, num_inference_steps):
+        self.num_inference_steps = num_inference_steps
+        ratio = self.num_train_timesteps // num_inference_steps
+        self.timesteps = torch.from_numpy((np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64))
+
+    def _coefficients(self, t):
+        t = int(t)
+        prev_t = t - self.num_train_timesteps // self.num_inference_steps
+        a_t = self.alphas_cumprod[t]
+        a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
+        # fp32 scalar arithmetic, as the 0-dim tensors of scheduler.step
+        return float((1 - a_t) ** 0.5), float(a_t ** 0.5), float(a_prev ** 0.5), float((1 - a_prev) ** 0.5)
+
+    def _launch(self, x, eps_u, eps_c, guidance, t):
+        x = x.detach().float().contiguous()
+        if eps_u.dtype not in (torch.float32, torch.bfloat16):
+            eps_u = eps_u.float()
+            eps_c = eps_c.float() if eps_c is not None else None
+        eps_u = eps_u.detach().contiguous()
+        eps_c = eps_c.detach().contiguous() if eps_c is not None else None
+        out = torch.empty_like(x)
+        c1, c2, c3, c4 = self._coefficients(t)
+        call("gd_ddim_step", ptr(x), ptr(eps_u), ptr(eps_c), int(eps_u.dtype == torch.bfloat16), float(guidance), c1, c2, c3, c4,
+             x.numel(), ptr(out), None, stream())
+        return out
+
+    def step(self, model_output, timestep, sample, eta=0.0):
+        """x_{t-1} (diffusion.py:55; formula restated at inversion.py:47-55)"""
+        assert eta == 0.0
+        return self._launch(sample, model_output, None, 0.0, timestep)
+
+    def step_cfg(self, eps_uncond, eps_text, guidance_scale, timestep, sample):
+        """eps = eps_u + g (eps_c - eps_u) (diffusion.py:46) fused with the step"""
+        return self._launch(sample, eps_uncond, eps_text, guidance_scale, timestep)
+
+    def inverse_coefficients(self, t):
+        """DDIM inversion x_t -> x_{t+1} (inversion.py:57-65): uses alpha at t and at t + ratio"""
+        t = int(t)
+        ratio = self.num_train_timesteps // self.num_inference_steps
+        cur_t, next_t = min(t - ratio, 999), t
+        a_t = self.alphas_cumprod[cur_t] if cur_t >= 0 else self.final_alpha_cumprod
+        a_next = self.alphas_cumprod[next_t]
+        return float((1 - a_t) ** 0.5), float(a_t ** 0.5), float(a_next ** 0.5), float((1 - a_next) ** 0.5)
+
+    def next_step(self, model_output, timestep, sample):
+        x = sample.detach().float().contiguous()
+        eps = model_output.detach().contiguous()
+        if eps.dtype not in (torch.float32, torch.bfloat16):
+            eps = eps.float()
+        out = torch.empty_like(x)
+        c1, c2, c3, c4 = self.inverse_coefficients(timestep)
+        call("gd_ddim_step", ptr(x), ptr(eps), None, int(eps.dtype == torch.bfloat16), 0.0, c1, c2, c3, c4, x.numel(), ptr(out), None, stream())
+        return out
+
+
+def diffusion_step(model, controller, latents, context, t, guidance_scale, low_resource=False, transform_coords=None, use_cfg=True,
+                   return_noise=False):
+    """diffusion.py:40-59.  With use_cfg=False the UNet runs under autograd (the caller enables grad) and the returned noise carries
+    the graph; the latent step itself is never differentiated by the reference loop (only controller.loss is, editor.py:273)."""
+    with torch.autocast("cuda", dtype=AUTOCAST_DTYPE):
+        if use_cfg:
+            latents_input = torch.cat([latents] * 2)
+            noise_pred = model.unet(latents_input, t, encoder_hidden_states=context)["sample"]
+            noise_pred_uncond, noise_prediction_text = noise_pred.chunk(2)
+            latents_out = model.scheduler.step_cfg(noise_pred_uncond, noise_prediction_text, guidance_scale, t, latents)
+            noise_pred_out = None
+            if return_noise:
+                noise_pred_out = noise_pred_uncond + guidance_scale * (noise_prediction_text - noise_pred_uncond)
+        else:
+            noise_pred_out = model.unet(latents, t, encoder_hidden_states=context)["sample"]
+            latents_out = model.scheduler.step(noise_pred_out, t, latents, eta=0.0)
+    latents_out = controller.step_callback(latents_out, transform_coords)
+    if return_noise:
+        return latents_out, noise_pred_out
+    return latents_out

@@ -1,0 +1,143 @@
+/*
+ * geodiffuser_b200.h -- C ABI of libgeodiffuser_b200.so: the B200 (sm_100a) implementation of GeoDiffuser's geometry-warped
+ * shared-attention hot path.  Plain pointers and sizes only; every pointer is a DEVICE pointer unless its name ends in `_host`;
+ * `stream` is a cudaStream_t; every function returns 0 on success or one of GD_ERR_* (message via gd_last_error()).
+ * No function allocates: outputs and workspaces are passed in.  Launches are asynchronous on `stream`.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to /root/reference/GeoDiffuser/utils/).
+ * The reference is pure Python, so the "FFI" a maintainer binds is ctypes: see INTEGRATION.md.
+ */
+#ifndef GEODIFFUSER_B200_H
+#define GEODIFFUSER_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GD_OK 0
+#define GD_ERR_INVALID 1
+#define GD_ERR_CUDA 2
+#define GD_ERR_UNSUPPORTED 3
+
+const char* gd_last_error(void);
+int gd_version(void);
+
+/* ---- (1) correspondence field, masks, splat index ------------------------------------------------------------------ */
+
+/* warp_utils.py:738-747 pixel2cam + :426-427 masked centroid.  depth, mask (H,W); Kinv9_host 3x3 row-major;
+ * cam (3,H,W) out; centroid4 = {cx, cy, cz, count} out.  Canonical reduction order: double, row-major (see oracle/geom_cpu.c). */
+int gd_corr_pixel2cam(const float* depth, const float* mask, int H, int W, const float* Kinv9_host, float* cam, float* centroid4,
+                      void* stream);
+
+/* warp_utils.py:599-643 cam2pixel_vanilla.  Rt12_host = top 3 rows of C^-1 T C; coords (H,W,3) = (x_norm, y_norm, Z) out. */
+int gd_corr_project(const float* cam, int H, int W, const float* Rt12_host, const float* K9_host, float* coords, void* stream);
+
+/* generic_torch.py:156-207 T.Resize(BILINEAR, antialias=False).  channels_last: src (Hin,Win,C) else (C,Hin,Win). */
+int gd_resize_bilinear(const float* src, int C, int Hin, int Win, int channels_last, float* dst, int Hout, int Wout, void* stream);
+
+/* attention_processors.py:338-360 mask algebra at resolution S from (Hin,Hin) planes; mask_new_warped / amodal_mask may be NULL
+ * (zeros: the Remover, :856-866).  out6 (6,S,S): mask_new_warped, mask_warp, amodal_mask, mask_intersection, mask_1_empty, mask_wo_edit */
+int gd_masks_build(const float* image_mask, const float* mask_new_warped, const float* amodal_mask, int Hin, int S, float* out6,
+                   void* stream);
+
+/* warp_utils.py:80-113 (pytorch3d rasterize_points).  coords (B,S,S,3); idx (B,S,S,K) int32 packed b*S*S+p, -1 = empty;
+ * zbuf (may be NULL), dist2 (B,S,S,K).  Order: z ascending, ties by packed index.  K <= 16. */
+int gd_splat_index(const float* coords, int B, int S, float radius_ndc, int K, int* idx, float* zbuf, float* dist2, void* stream);
+
+/* warp_utils.py:131-176 (alpha weights + pytorch3d alpha_composite + .half()).  dtype: 0 fp32, 1 bf16.
+ * layout: 0 (B,C,P) channel-first, 1 (B,P,C) channel-last.  idx/dist2 (Bi,P,K), Bi in {1,B}.  blend_mask (P) or NULL:
+ * out = src*(1-m) + m*warped (attention_processors.py:544).  post: 0 none, 1 binarize(>0.5) (generic_torch.py:122). */
+int gd_splat_composite(const void* src, int src_dtype, int layout, const int* idx, const float* dist2, int Bi, int B, int P, int C,
+                       int K, float r2, float tau, const float* blend_mask, int post, void* out, int out_dtype, void* stream);
+
+/* warp_utils.py:364-399 get_mesh + :235-298 splatter_mesh (pytorch3d rasterize_meshes): coverage of the object's depth mesh. */
+int gd_mesh_mask(const float* coords, const float* mask, int H, int W, float blur, float* out, void* stream);
+
+/* generic_torch.py:210-235 torch_erode (mode 0) / torch_dilate (mode 1), k x k window, zero padding.  src/dst (B,H,W). */
+int gd_morph(const float* src, int B, int H, int W, int kernel, int mode, float* dst, void* stream);
+
+/* ---- (2) shared attention forward ---------------------------------------------------------------------------------- */
+
+/* attention_sharing.py:30-47 compute_attention + torch.bmm(P,V) (attention_processors.py:427-433, 548-557, 643-647).
+ * G query streams q[g] (H,N,d) bf16, each against k[g], v[g] (H,Nk,d) bf16 -> o[g] (H,N,d) fp32, lse[g] (H,N) fp32 (natural log).
+ * The five arrays are HOST arrays of G device pointers; G <= 8; d % 8 == 0, d <= 160.  Any N, Nk. */
+int gd_attn_fwd_generic(const void* const* q_host, const void* const* k_host, const void* const* v_host, void* const* o_host,
+                        void* const* lse_host, int G, int H, int N, int Nk, int d, float scale, void* stream);
+
+/* Same contract, tcgen05 / TMEM / TMA kernel for the large self-attention levels: N == Nk, N % 128 == 0, d in {40, 80}. */
+int gd_attn_fwd_sm100(const void* const* q_host, const void* const* k_host, const void* const* v_host, void* const* o_host,
+                      void* const* lse_host, int G, int H, int N, int Nk, int d, float scale, void* stream);
+
+/* ---- (3) backward, fused with the attention-map losses --------------------------------------------------------------- */
+
+/* dO = g_out * coef[row] + g_loss * (*loss_scale) (bf16 out), delta[h,row] = sum_c dO*O (+ delta_extra[h, rowmap[row]] * *loss_scale).
+ * g_out (H,N,d) fp32/bf16 or NULL; coef (N) or NULL; g_loss (H,N,d) fp32 or NULL; loss_scale: device scalar or NULL (=1). */
+int gd_attn_bwd_prep(const void* g_out, int g_out_is_bf16, const float* coef, const float* g_loss, const float* loss_scale,
+                     const float* o, const float* delta_extra, const int* rowmap, int M, int H, int N, int d, void* d_o_bf16,
+                     float* delta, void* stream);
+
+/* What torch autograd derives for softmax(scale q k^T) v (attention_sharing.py:35-45).  mode 0: out = dQ (H,N,d); mode 1: out = dK
+ * (H,Nk,d).  extra (H,M,ex_ld) fp32 = dL/dP rows for the queries with rowmap[row] >= 0 (removal loss), scaled by *extra_scale. */
+int gd_attn_bwd(int mode, const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
+                const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* out, int H, int N, int Nk,
+                int d, float scale, void* stream);
+
+int gd_cast_f32_to_bf16(const float* src, void* dst_bf16, long n, void* stream);
+
+/* P[h,m,:] = softmax row of q[h, rows[m] or m] against k[h] given lse (bf16 out, row stride ldp % 8 == 0, pad columns zero).
+ * Materialises the maps removal_loss_geodiff consumes (attention_processors.py:250). */
+int gd_attn_probs(const void* q, const void* k, const float* lse, const int* rows, int M, int H, int N, int Nk, int d, float scale,
+                  void* p_out_bf16, int ldp, void* stream);
+
+/* attention_processors.py:250-258: corr = A_e[rows] A_b^T, masked max / arg-max per 64-wide tile of columns.
+ * partial (H, ceil(Nb/64), M, 4) = {max_in, argmax_in (int bits), max_bg, argmax_bg (int bits)}. */
+int gd_corr_max_partial(const void* a_e_bf16, const void* a_b_bf16, int H, int M, int Nb, int Nk, int ld, const float* mask_in,
+                        const float* mask_bg, float* partial, void* stream);
+
+/* attention_processors.py:231-246 (sim), 283-287 (movement), 289-305 (amodal, target t), loss.py:22-41 (smoothness): unweighted partial
+ * sums (n_partials,5) and grad = d(weighted loss)/d replace_out.  c_* = weight / denominator of each term. */
+int gd_attn_l1_losses(const float* e, const float* r, const float* t, const float* m_bg, const float* m_edit, const float* m_am,
+                      const float* w_am, float c_sim, float c_mov, float c_amo, float c_smh, float c_smw, int H, int S, int d,
+                      float* grad, float* partials, int n_partials, void* stream);
+
+/* attention_processors.py:259-266: distance weight, log terms, and the two non-zero gradient entries per row; extra (H,M,ld) and
+ * delta_extra (H,M) feed gd_attn_bwd_prep / gd_attn_bwd.  coef = removal weight / (sum(mask_inpaint) * H + 1e-8). */
+int gd_removal_finalize(const float* partial, int n_tiles, int H, int M, int S, const int* rows, const float* mask_in,
+                        const float* mask_bg, float coef, const void* a_b_bf16, int Nb, int Nk, int ld, float* term, float* g2, int* j2,
+                        float* delta_extra, float* extra, void* stream);
+
+/* terms6 = {sim, movement, removal, smoothness, amodal, weighted total}; terms_accum6 (or NULL) += terms6.
+ * inv6_host = 1/denominators {sim, movement, amodal, smooth_h, smooth_w, removal}; w5_host = weights {sim, movement, amodal, smoothness, removal} */
+int gd_loss_reduce(const float* partials, int n_part, const float* rem_terms, int n_rem, const float* inv6_host, const float* w5_host,
+                   float amodal_gate, float* terms6, float* terms_accum6, void* stream);
+
+/* attention_sharing.py:68-105 interpolate_from_mask: nearest-4 foreground pixels + weights (mask/grid only: once per resolution). */
+int gd_amodal_knn(const float* m_edit, int S, int* idx4, float* val4, float* w, void* stream);
+
+/* attention_processors.py:291-293 + generic_torch.py:145-154: interpolated, foreground-overwritten, 5x5-gaussian-smoothed target. */
+int gd_amodal_target(const float* e, const float* m_edit, const int* idx4, const float* val4, const float* gauss25_host, int H, int S,
+                     int d, float* scratch, float* target, void* stream);
+
+/* attention_processors.py:617-624, 922-925: out = a * ma[row] + b * mb[row] (a may be NULL; mb NULL = 1). */
+int gd_blend_rows(const float* a, const float* ma, const float* b, const float* mb, int H, int N, int d, void* out, int out_is_bf16,
+                  void* stream);
+
+/* ---- (4) DDIM step and latent update ------------------------------------------------------------------------------- */
+
+/* diffusion.py:46,55: eps = eps_u + g (eps_c - eps_u) if eps_c; x_prev = sqrt(a_prev) (x - sqrt(1-a_t) eps)/sqrt(a_t) + sqrt(1-a_prev) eps */
+int gd_ddim_step(const float* x, const void* eps_u, const void* eps_c, int eps_is_bf16, float guidance, float sqrt_one_minus_at,
+                 float sqrt_at, float sqrt_aprev, float sqrt_one_minus_aprev, long n, float* out, float* eps_out, void* stream);
+
+/* optimization.py:213-245: nan_to_num(grad); out = (lat - 2 m s g) - (1 - m) s g, m (hw) broadcast over channels (NULL: lat - s g). */
+int gd_latent_update(const float* lat, const float* grad, const float* mask, int hw, float step, long n, float* out, void* stream);
+
+/* editor.py:219,316 + generic_torch.py:87: norm_out = sqrt(sum x^2 + 1e-12); if target_norm > 0: x *= target_norm / norm. */
+int gd_norm_rescale(float* x, long n, float target_norm, float* norm_out, void* stream);
+
+/* editor.py:393-399: out = a (1 - m) + m b, m optionally binarised (> 0.5). */
+int gd_latent_blend(const float* a, const float* b, const float* mask, int hw, int binarize, long n, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,120 @@
+"""GPU parity of subsystems (2)+(3) through the reference-facing controller API: the same calls oracle/make_golden.py made on the
+reference's own AttentionGeometryEdit / AttentionGeometryRemover, compared with the committed golden outputs, loss terms and
+gradients.  Tolerance: 2e-2 relative (BF16 kernels vs the reference's FP32), the bound BASELINE.json states."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, relerr
+from geodiffuser_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-2
+
+CASES = [  # name, geometry, kind, S, H, d, is_cross, use_cfg, seed, cur_step   (oracle/make_golden.py:main)
+    ("edit_self_S32_opt", "translate2d", "edit", 32, 2, 16, False, False, 101, 0),
+    ("edit_self_S64_opt", "rotate3d", "edit", 64, 1, 8, False, False, 102, 0),
+    ("edit_cross_S32_opt", "translate2d", "edit", 32, 2, 16, True, False, 103, 0),
+    ("edit_self_S32_cfg", "rotate3d", "edit", 32, 2, 16, False, True, 104, 0),
+    ("edit_self_S16_cfg_late", "translate2d", "edit", 16, 2, 32, False, True, 105, 46),
+    ("edit_cross_S16_cfg", "translate2d", "edit", 16, 2, 32, True, True, 106, 0),
+    ("remove_self_S32_opt", "remove", "remove", 32, 2, 16, False, False, 107, 0),
+    ("remove_cross_S32_opt", "remove", "remove", 32, 2, 16, True, False, 108, 0),
+    ("remove_self_S32_cfg_late", "remove", "remove", 32, 2, 16, False, True, 109, 46),
+]
+
+_GEO = {}
+
+
+def geometry_for(kind):
+    from geodiffuser_b200 import geometry as G
+
+    if kind not in _GEO:
+        image, depth, mask, T = synth.edit_inputs(kind)
+        g = G.correspondence_field(depth.copy(), mask.copy(), T)
+        amodal = G.torch_erode(G.mesh_mask(g["coords"], g["mask"])[None, None])
+        _GEO[kind] = dict(coords=g["coords"][None], mask=mask.astype(np.float32), amodal=amodal)
+    return _GEO[kind]
+
+
+def make_controller(kind, geo, cur_step, use_cfg):
+    from geodiffuser_b200 import attention_processors as AP
+
+    cls = AP.AttentionGeometryEdit if kind == "edit" else AP.AttentionGeometryRemover
+    c = cls(["", ""], 50, cross_replace_steps={"default_": 0.95}, self_replace_steps=0.95, image_mask=geo["mask"], empty_scale=0.0,
+            use_all=False, obj_edit_step=0.9, tokenizer=None, device="cuda", mode="bilinear")
+    c.num_att_layers = 32
+    c.amodal_mask = geo["amodal"]
+    c.cur_step = cur_step
+    c.use_cfg = use_cfg
+    c.coords_base, c.coords_edit = ((2, 3), (3, 4)) if use_cfg else ((0, 1), (1, 2))
+    return c
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_controller_matches_reference_golden(case):
+    name, gname, kind, S, H, d, is_cross, use_cfg, seed, cur_step = case
+    z = np.load(os.path.join(GOLDEN, f"attn_{name}.npz"))
+    geo = geometry_for(gname)
+    c = make_controller(kind, geo, cur_step, use_cfg)
+    B = 4 if use_cfg else 2
+    q, k, v = synth.qkv(seed, B, H, S * S, 77 if is_cross else S * S, d)
+    q, k, v = (torch.from_numpy(a).cuda().requires_grad_(not use_cfg) for a in (q, k, v))
+    with torch.set_grad_enabled(not use_cfg):
+        out = c(q, k, v, is_cross, "down", transform_coords=geo["coords"], scale=d ** -0.5, mask=None)
+    assert out.shape == q.shape
+    assert relerr(out.detach().float().cpu().numpy(), z["out"]) <= TOL
+    assert c.cur_att_layer == 1
+    if "loss" in z.files:
+        loss = c.loss
+        assert abs(float(loss) - float(z["loss"])) <= TOL * abs(float(z["loss"])) + 1e-3
+        att = "cross" if is_cross else "self"
+        for key, val in c.loss_log_dict[att].items():
+            ref = float(z["term_" + key])
+            assert abs(float(val) - ref) <= TOL * max(abs(ref), 0.05), (key, float(val), ref)
+        gq, gk = torch.autograd.grad(loss + 0.37 * out.float().sum(), [q, k], allow_unused=True)
+        assert relerr(gq.cpu().numpy(), z["dq"]) <= TOL
+        if "dk" in z.files:
+            assert gk is not None
+            assert relerr(gk.cpu().numpy(), z["dk"]) <= TOL
+        # base half of the batch carries no gradient (attention_sharing.py:242)
+        assert float(gq[: H].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("N,Nk,d", [(4096, 4096, 40), (1024, 1024, 80), (256, 256, 160), (64, 64, 160), (4096, 77, 40), (1024, 77, 80),
+                                    (576, 576, 160), (200, 77, 40)])
+def test_attention_forward_vs_fp32(N, Nk, d):
+    """softmax(QK^T)V against a plain fp32 torch evaluation on the SAME bf16-rounded inputs, at the UNet's real shapes
+    (N in {4096,1024,256,64}, d in {40,80,160}, 77 text keys; 576 = a 768^2 level; 200 = ragged)."""
+    from geodiffuser_b200 import functional as Fn
+
+    g = torch.Generator(device="cuda").manual_seed(N + d)
+    H = 8 if N * Nk <= 4096 * 4096 // 4 else 2
+    q = torch.randn(H, N, d, device="cuda", generator=g).bfloat16()
+    k = torch.randn(H, Nk, d, device="cuda", generator=g).bfloat16()
+    v = torch.randn(H, Nk, d, device="cuda", generator=g).bfloat16()
+    scale = d ** -0.5
+    O, LSE = Fn.attention_forward([q], [k], [v], scale)
+    s = torch.einsum("hnd,hkd->hnk", q.float(), k.float()) * scale
+    ref = torch.softmax(s, -1) @ v.float()
+    assert relerr(O[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2
+    assert relerr(LSE[0].cpu().numpy(), torch.logsumexp(s, -1).cpu().numpy()) <= 1e-3
+
+
+def test_plain_attention_outside_window_and_counters():
+    """after the self-replace window (cur_step >= 47) self layers run plain attention on the whole batch
+    (attention_processors.py:646-647); the layer / step counters advance as attention_sharing.py:139-143"""
+    geo = geometry_for("translate2d")
+    c = make_controller("edit", geo, 48, True)
+    c.num_att_layers = 2
+    H, S, d = 2, 16, 32
+    q, k, v = (torch.from_numpy(a).cuda() for a in synth.qkv(5, 4, H, S * S, S * S, d))
+    with torch.no_grad():
+        out = c(q, k, v, False, "up", transform_coords=geo["coords"], scale=d ** -0.5)
+        ref = torch.softmax(torch.einsum("bnd,bkd->bnk", q, k) * d ** -0.5, -1) @ v
+        assert relerr(out.cpu().numpy(), ref.cpu().numpy()) <= TOL
+        assert (c.cur_att_layer, c.cur_step) == (1, 48)
+        c(q, k, v, False, "up", transform_coords=geo["coords"], scale=d ** -0.5)
+        assert (c.cur_att_layer, c.cur_step) == (0, 49)
