@@ -21,5 +21,5 @@ if [ $fail -ne 0 ]; then
     grep -h -E "error|Error" -A3 _obj/*.log || cat _obj/*.log
     exit 1
 fi
-$NVCC $ARCH -shared -o $OUT _obj/*.o -lcudart -lcuda
+$NVCC $ARCH -shared -o $OUT _obj/*.o
 echo "built $(cd .. && pwd)/libgeodiffuser_b200.so"

@@ -32,7 +32,7 @@ class DDIMScheduler:
         # fp32 scalar arithmetic, as the 0-dim tensors of scheduler.step
         return float((1 - a_t) ** 0.5), float(a_t ** 0.5), float(a_prev ** 0.5), float((1 - a_prev) ** 0.5)
 
-    def _launch(self, x, eps_u, eps_c, guidance, t):
+    def _launch(self, x, eps_u, eps_c, guidance, coef):
         x = x.detach().float().contiguous()
         if eps_u.dtype not in (torch.float32, torch.bfloat16):
             eps_u = eps_u.float()
@@ -40,7 +40,7 @@ class DDIMScheduler:
         eps_u = eps_u.detach().contiguous()
         eps_c = eps_c.detach().contiguous() if eps_c is not None else None
         out = torch.empty_like(x)
-        c1, c2, c3, c4 = self._coefficients(t)
+        c1, c2, c3, c4 = coef
         call("gd_ddim_step", ptr(x), ptr(eps_u), ptr(eps_c), int(eps_u.dtype == torch.bfloat16), float(guidance), c1, c2, c3, c4,
              x.numel(), ptr(out), None, stream())
         return out
@@ -48,30 +48,27 @@ class DDIMScheduler:
     def step(self, model_output, timestep, sample, eta=0.0):
         """x_{t-1} (diffusion.py:55; formula restated at inversion.py:47-55)"""
         assert eta == 0.0
-        return self._launch(sample, model_output, None, 0.0, timestep)
+        return self._launch(sample, model_output, None, 0.0, self._coefficients(timestep))
 
     def step_cfg(self, eps_uncond, eps_text, guidance_scale, timestep, sample):
         """eps = eps_u + g (eps_c - eps_u) (diffusion.py:46) fused with the step"""
-        return self._launch(sample, eps_uncond, eps_text, guidance_scale, timestep)
+        return self._launch(sample, eps_uncond, eps_text, guidance_scale, self._coefficients(timestep))
 
     def inverse_coefficients(self, t):
-        """DDIM inversion x_t -> x_{t+1} (inversion.py:57-65): uses alpha at t and at t + ratio"""
+        """DDIM inversion x_t -> x_{t+1} (diffusers-0.25 DDIMInverseScheduler.step as used at inversion.py:145-186; same algebra as
+        inversion.py:57-65): alpha at t - ratio (1.0 before the first step) and at t"""
         t = int(t)
         ratio = self.num_train_timesteps // self.num_inference_steps
-        cur_t, next_t = min(t - ratio, 999), t
-        a_t = self.alphas_cumprod[cur_t] if cur_t >= 0 else self.final_alpha_cumprod
-        a_next = self.alphas_cumprod[next_t]
+        cur_t = min(t - ratio, self.num_train_timesteps - 1)
+        a_t = self.alphas_cumprod[cur_t] if cur_t >= 0 else torch.tensor(1.0)
+        a_next = self.alphas_cumprod[t]
         return float((1 - a_t) ** 0.5), float(a_t ** 0.5), float(a_next ** 0.5), float((1 - a_next) ** 0.5)
 
     def next_step(self, model_output, timestep, sample):
-        x = sample.detach().float().contiguous()
-        eps = model_output.detach().contiguous()
-        if eps.dtype not in (torch.float32, torch.bfloat16):
-            eps = eps.float()
-        out = torch.empty_like(x)
-        c1, c2, c3, c4 = self.inverse_coefficients(timestep)
-        call("gd_ddim_step", ptr(x), ptr(eps), None, int(eps.dtype == torch.bfloat16), 0.0, c1, c2, c3, c4, x.numel(), ptr(out), None, stream())
-        return out
+        return self._launch(sample, model_output, None, 0.0, self.inverse_coefficients(timestep))
+
+    def next_step_cfg(self, eps_uncond, eps_text, guidance_scale, timestep, sample):
+        return self._launch(sample, eps_uncond, eps_text, guidance_scale, self.inverse_coefficients(timestep))
 
 
 def diffusion_step(model, controller, latents, context, t, guidance_scale, low_resource=False, transform_coords=None, use_cfg=True,

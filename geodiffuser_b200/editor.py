@@ -1,0 +1,227 @@
+"""The DDIM edit loop around the hot path, restated from /root/reference/GeoDiffuser/utils/editor.py:65-423
+(`text2image_ldm_stable`), inversion.py:131-196 (`ddim_loop`) and generic.py:34-60 (loss-log helpers), with the per-edit-type
+hyper-parameters of large_scale_editor.py:199-299 (`perform_exp`).  Text encoder / VAE / image post-processing are out of scope
+(SURVEY 2 rows 8, 12): prompts are replaced by synthetic context embeddings and images by synthetic latents.
+
+Control flow, step conditions, learning-rate schedule, norm preservation, reference-latent replacement and the latent warp are the
+reference's; every tensor op on the path is a C-ABI CUDA launch (attention layers, DDIM step, update, warp), the UNet body is stock torch.
+"""
+import numpy as np
+import torch
+
+from . import geometry, synth
+from .attention_processors import (AttentionGeometryEdit, AttentionGeometryRemover, VanillaAttentionProcessor,
+                                   register_attention_control_diffusers, set_attn_processor_for_edit)
+from .diffusion import AUTOCAST_DTYPE, diffusion_step
+from .optimization import (_update_latent, adaptive_optimization_step_editing, adaptive_optimization_step_remover, norm_tensor,
+                           rescale_to_norm_)
+from ._lib import call, ptr, stream
+
+NUM_DDIM_STEPS = 50
+IMAGE_SIZE = 512
+SEED = 1234  # editor.py:47
+
+
+def clear_controller_loss(controller):
+    """generic.py:41-47"""
+    controller.loss = 0.0
+    if controller.loss_log_dict is not None:
+        controller.initialize_loss_log_dict()
+
+
+def convert_loss_log_to_numpy(loss_log_dict):
+    """generic.py:50-60 (one small D2H per logged term, as the reference's .item() calls)"""
+    out = {"self": {}, "cross": {}}
+    for att_type in loss_log_dict:
+        if att_type in ("self", "cross"):
+            for key in loss_log_dict[att_type]:
+                v = loss_log_dict[att_type][key]
+                out[att_type][key] = v.item() if torch.is_tensor(v) else float(v)
+        else:
+            out[att_type] = loss_log_dict[att_type]
+    return out
+
+
+@torch.no_grad()
+def ddim_inversion_loop(model, latent, context, guidance_scale=3.0, num_ddim_steps=NUM_DDIM_STEPS):
+    """inversion.py:131-196: x_0 -> [x_0, x_1, ..., x_T] with classifier-free guidance and vanilla attention (N1 in SURVEY 8(f))."""
+    model.unet.set_attn_processor(VanillaAttentionProcessor())
+    sched = model.scheduler
+    sched.set_timesteps(num_ddim_steps)
+    all_latent = [latent]
+    latents = latent.clone().detach().float()
+    for t in reversed(sched.timesteps.tolist()):  # 0, 20, ..., 980 (DDIMInverseScheduler, leading spacing)
+        with torch.autocast("cuda", dtype=AUTOCAST_DTYPE):
+            noise_pred = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
+        eu, ec = noise_pred.chunk(2)
+        latents = sched.next_step_cfg(eu, ec, guidance_scale, t, latents)
+        all_latent.append(latents.detach())
+    return all_latent
+
+
+@torch.no_grad()
+def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, guidance_scale=7.5, generator=None, latent=None,
+                          uncond_embeddings=None, text_embeddings=None, start_time=50, return_type="latent",
+                          transform_coordinates=None, mask_obj=None, optimize_steps=0.2, latent_replace=0.2, lr=0.0,
+                          optimize_embeddings=False, optimize_latents=False, ddim_latents=None, ddim_noise=None,
+                          edit_type="geometry_editor", fast_start_steps=0.0, num_first_optim_steps=5, use_adaptive_optimization=True,
+                          adain_latents_steps=0.95, use_optimizer=False, removal_loss_value_in=-1.5, skip_optim_steps=2,
+                          progress=None):
+    """editor.py:65-423.  `uncond_embeddings` / `text_embeddings`: (B,77,768) tensors standing in for the CLIP encodings (:106-121).
+    Returns (latents, x_T, global_loss_log_dict)."""
+    if edit_type not in ("geometry_editor", "geometry_remover"):
+        raise NotImplementedError(edit_type)  # the stitch controllers do not exist in the reference either
+    if use_optimizer:
+        raise NotImplementedError("use_optimizer is never forwarded by the reference drivers (editor.py:651-652)")
+    global_loss_log_dict = {}
+    batch_size = len(prompt)
+    device = model.device
+    register_attention_control_diffusers(model, controller, transform_coordinates)
+    text_embeddings = text_embeddings.to(device).float()
+    uncond_embeddings_ = uncond_embeddings.to(device).float()
+    latents = latent[:1].expand(batch_size, *latent.shape[1:]).to(device).float().contiguous()
+    model.scheduler.set_timesteps(num_inference_steps)
+    timesteps = model.scheduler.timesteps[-start_time:].tolist()
+    n_t = len(timesteps)
+    context_save = None
+    first_optim_complete = False
+    if transform_coordinates is not None and hasattr(controller, "_ensure_mask_new_warped"):
+        controller._ensure_mask_new_warped(transform_coordinates, device)  # editor.py:147-149
+    is_remover = type(controller).__name__ == "AttentionGeometryRemover"
+
+    for i, t in enumerate(timesteps):
+        context = torch.cat([uncond_embeddings_, text_embeddings])
+        clear_controller_loss(controller)
+        do_opt = (i < optimize_steps * n_t) and (i % skip_optim_steps == 0) and (i >= fast_start_steps * n_t)
+        if do_opt:
+            if not first_optim_complete and fast_start_steps > 0.0:
+                num_optim_steps, first_optim_complete = num_first_optim_steps, True
+            else:
+                num_optim_steps = 1
+            best_loss, best_latents, best_context = 1e8, None, None
+            l_eff = lr * (50 - i) * skip_optim_steps * (50 / (NUM_DDIM_STEPS + 1e-8))  # editor.py:207
+            set_attn_processor_for_edit(model, coords_base=(0, 1), coords_edit=(1, 2), use_cfg=False)
+            latents_in = latents.detach().float().requires_grad_(True)
+            orig_norm = norm_tensor(latents_in[-1:].detach())
+            context_in = (context if context_save is None else context_save).detach().float().requires_grad_(True)
+            for _ in range(num_optim_steps):
+                with torch.enable_grad():
+                    _, _ = diffusion_step(model, controller, latents_in, context_in[2:], t, guidance_scale, transform_coords=transform_coordinates,
+                                          use_cfg=False, return_noise=True)
+                    loss_val = controller.loss.detach().item()
+                    if loss_val < best_loss:
+                        best_latents, best_context, best_loss = latents_in, context_in, loss_val
+                    latents_in, context_new = _update_latent(latents_in, controller.loss, l_eff, controller.mask_new_warped[:1], context_in)
+                    if num_optim_steps == 1:
+                        best_latents, best_context = latents_in, context_new
+                    context_in = context_new.detach().float().requires_grad_(True)
+                    latents_in = latents_in.detach().float().requires_grad_(True)
+                    out_log = convert_loss_log_to_numpy(controller.loss_log_dict)
+                    if use_adaptive_optimization:
+                        fn = adaptive_optimization_step_remover if is_remover else adaptive_optimization_step_editing
+                        fn(controller, i, skip_optim_steps, out_log, num_ddim_steps=NUM_DDIM_STEPS, removal_loss_value_in=removal_loss_value_in)
+                    out_log["loss"] = loss_val
+                    global_loss_log_dict[i] = out_log
+                    clear_controller_loss(controller)
+                    controller.cur_step -= 1
+            if optimize_latents:
+                latents = best_latents.detach().clone()
+                rescale_to_norm_(latents[-1], orig_norm)  # editor.py:316
+            if best_context is not None and optimize_embeddings:
+                context = best_context.detach()
+                context_save = context
+        elif i < fast_start_steps * n_t:
+            continue
+        elif context_save is not None:
+            context = context_save
+        set_attn_processor_for_edit(model, coords_base=(2, 3), coords_edit=(3, 4), use_cfg=True)
+        latents = diffusion_step(model, controller, latents, context, t, guidance_scale, transform_coords=transform_coordinates)
+        if ddim_latents is not None:
+            i_n = len(ddim_latents) - 2 - i
+            latents = torch.cat([ddim_latents[i_n].to(latents), latents[-1:].detach()], 0)  # editor.py:375-377
+        if progress is not None:
+            progress(i / NUM_DDIM_STEPS)
+        if not is_remover and ((i < n_t * latent_replace and mask_obj is not None) or (i < n_t * fast_start_steps)):
+            latents = _latent_warp_replace(controller, latents, transform_coordinates, fast=i < n_t * fast_start_steps)
+    return latents, latent, global_loss_log_dict
+
+
+def _latent_warp_replace(controller, latents, transform_coordinates, fast=False):
+    """editor.py:382-399: paste the reference latent, splat-warped through the 64^2 correspondence field, inside the warped mask."""
+    S = latents.shape[-1]
+    dev = latents.device
+    cache = controller._get_cache(S, transform_coordinates, dev)  # same coords@S / splat index the attention layers use
+    m = geometry.resize_bilinear(controller.mask_new_warped[:1].float().contiguous(), S)[0, 0].contiguous()
+    src = latents[-2:-1].detach().float().contiguous()
+    warped = geometry.splat_composite(src, cache.idx, cache.dist2)
+    out = latents.clone()
+    base = latents[:1] if fast else latents[-1:]
+    call("gd_latent_blend", ptr(base.contiguous()), ptr(warped), ptr(m), S * S, 1, warped.numel(), ptr(out[-1]), stream())
+    return out
+
+
+# hyper-parameters of large_scale_editor.perform_exp (:199-299) per edit type -- the canonical benchmark settings
+EXP_PARAMS = {
+    "geometry_editor": dict(cross_replace_steps={"default_": 0.95}, self_replace_steps=0.95, optimize_steps=0.65, lr=0.03,
+                            latent_replace=0.1, optimize_embeddings=True, optimize_latents=True, obj_edit_step=0.9, skip_optim_steps=2,
+                            guidance_scale=3.0,
+                            loss_weights_dict={"self": {"sim": 55, "movement": 30.5, "removal": 2.6, "smoothness": 30.0, "amodal": 80.5},
+                                               "cross": {"sim": 45, "movement": 30.34, "removal": 2.6, "smoothness": 15.0, "amodal": 3.5}}),
+    "geometry_remover": dict(cross_replace_steps={"default_": 0.9}, self_replace_steps=0.9, optimize_steps=0.85, lr=0.03,
+                             latent_replace=0.4, optimize_embeddings=True, optimize_latents=True, obj_edit_step=1.0, skip_optim_steps=2,
+                             guidance_scale=5.0,
+                             loss_weights_dict={"self": {"sim": 55, "removal": 4.6, "smoothness": 30.0},
+                                                "cross": {"sim": 45, "removal": 4.6, "smoothness": 15.0}}),
+}
+
+
+def synthetic_embeddings(seed=SEED, device="cuda"):
+    """context stand-ins: randn(2,77,768) text + randn uncond, CPU generator so every box sees the same values"""
+    g = torch.Generator().manual_seed(seed + 1)
+    text = torch.randn(1, 77, 768, generator=g).expand(2, 77, 768).contiguous()
+    uncond = torch.randn(1, 77, 768, generator=g).expand(2, 77, 768).contiguous()
+    x0 = torch.randn(1, 4, IMAGE_SIZE // 8, IMAGE_SIZE // 8, generator=g)
+    return text.to(device), uncond.to(device), x0.to(device)
+
+
+def perform_geometric_edit(model, kind="rotate3d", num_ddim_steps=NUM_DDIM_STEPS, perform_ddim_inversion=True, seed=SEED, return_log=False,
+                           **overrides):
+    """editor.py:428-711 on synthetic inputs: correspondence field -> (DDIM inversion) -> controller -> edit loop.
+    kind in synth.EDIT_KINDS; returns the final (2,4,64,64) latents [reference, edited]."""
+    global NUM_DDIM_STEPS
+    NUM_DDIM_STEPS = num_ddim_steps
+    device = model.device
+    edit_type = "geometry_remover" if kind == "remove" else "geometry_editor"
+    hp = dict(EXP_PARAMS[edit_type])
+    hp.update(overrides)
+    image, depth, mask, T = synth.edit_inputs(kind)
+    t_coords, _, amodal = geometry.get_transform_coordinates(image / 255.0, depth, mask, T, return_mesh=True, device=device)
+    g = geometry.get_transform_coordinates.last
+    transform_coordinates = g["coords"][None]  # stays on the device (the reference round-trips through numpy, editor.py:546-547)
+    text, uncond, x0 = synthetic_embeddings(seed, device)
+    model.scheduler.set_timesteps(num_ddim_steps)
+    if perform_ddim_inversion:
+        ddim_latents = ddim_inversion_loop(model, x0, torch.cat([uncond[:1], text[:1]]), hp["guidance_scale"], num_ddim_steps)
+    else:
+        gen = torch.Generator().manual_seed(seed + 2)
+        ddim_latents = [x0] + [torch.randn(1, 4, 64, 64, generator=gen).to(device) for _ in range(num_ddim_steps)]
+    x_t = ddim_latents[-1]
+    cls = AttentionGeometryRemover if edit_type == "geometry_remover" else AttentionGeometryEdit
+    controller = cls(["", ""], num_ddim_steps, cross_replace_steps=hp["cross_replace_steps"], self_replace_steps=hp["self_replace_steps"],
+                     image_mask=mask.astype(np.float32), empty_scale=0.0, use_all=False, obj_edit_step=hp["obj_edit_step"], device=device)
+    controller.amodal_mask = geometry.torch_erode(g["mesh_mask"][None, None])  # editor.py:633
+    if hp.get("loss_weights_dict") is not None:
+        import copy
+        lw = copy.deepcopy(hp["loss_weights_dict"])
+        controller.loss_weight_dict = lw
+        controller.default_loss_weights = lw  # aliased exactly like editor.py:637-638
+    latents, _, log = text2image_ldm_stable(
+        model, ["", ""], controller, num_inference_steps=num_ddim_steps, guidance_scale=hp["guidance_scale"], latent=x_t,
+        uncond_embeddings=uncond, text_embeddings=text, transform_coordinates=transform_coordinates,
+        mask_obj=torch.from_numpy(mask.astype(np.float32))[None, None], optimize_steps=hp["optimize_steps"], latent_replace=hp["latent_replace"],
+        lr=hp["lr"], optimize_embeddings=hp["optimize_embeddings"], optimize_latents=hp["optimize_latents"], ddim_latents=ddim_latents,
+        edit_type=edit_type, skip_optim_steps=hp["skip_optim_steps"], removal_loss_value_in=hp.get("removal_loss_value_in", -1.5))
+    model.unet.set_attn_processor(VanillaAttentionProcessor())  # editor.py:698
+    if return_log:
+        return latents, log
+    return latents
