@@ -24,6 +24,7 @@ SIGNATURES = {
     "gd_mesh_mask": [P, P, I, I, F, P, P],
     "gd_morph": [P, I, I, I, I, I, P, P],
     "gd_attn_fwd_generic": [P, P, P, P, P, I, I, I, I, I, F, P],
+    "gd_attn_fwd_sm100": [P, P, P, P, P, I, I, I, I, I, F, P],
     "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, I, I, I, I, P, P, P],
     "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P],
     "gd_cast_f32_to_bf16": [P, P, L, P],

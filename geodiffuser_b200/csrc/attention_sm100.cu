@@ -1,0 +1,404 @@
+// geodiffuser_b200/csrc/attention_sm100.cu
+//
+// Subsystem (2): fused flash-style shared-attention FORWARD for sm_100a, for the self-attention levels that dominate the
+// path (N = Nk in {4096, 1024, 9216, 2304}, head_dim 40 / 80).  Replaces attention_sharing.py:30-47 (`compute_attention`:
+// baddbmm -> fp32 softmax over a materialised (H, N, N) map) + torch.bmm(P, V) at attention_processors.py:548-557, 643-647.
+//
+// One CTA = one (stream g, head h, 128-query tile); 192 threads in three roles:
+//   warps 0-3  softmax / correction / epilogue: thread t owns query row t == TMEM lane t
+//   warp  4    TMA producer: Q once, then K / V tiles of 128 keys through a 2-stage mbarrier ring (cp.async.bulk.tensor, SWIZZLE_128B)
+//   warp  5    MMA issuer (one elected lane): S = Q K^T  (tcgen05.mma, A/B from shared memory, fp32 accumulator in TMEM),
+//                                              O += P V   (A = bf16 P read from TMEM, B = V from shared memory, MN-major)
+// TMEM columns: [0,128) S  |  [128,192) P (bf16 pairs)  |  [192, 192+DV) O.   S is consumed into registers and released before the
+// exponentials run, so QK^T of tile j+1 overlaps softmax of tile j; O is rescaled in TMEM only when the running max grows by more
+// than 2^8 (lazy rescaling), which is exact after the final normalisation.  head_dim 40: two CTAs per SM (80 KB smem, 256 TMEM
+// columns each) so one CTA's MMAs fill the other's softmax phase.
+//
+// Roofline: tensor pipe (dense BF16) -- but at head_dim 40 a 128x128 tile costs 16384 exp2 (MUFU, 16/clk/SM = 1024 clk) against
+// ~384 clk of UMMA, so this shape is bounded by the special-function unit, not the tensor cores.
+#include <cuda.h>
+#include "common.cuh"
+
+namespace gd {
+
+typedef __nv_bfloat16 bf16;
+constexpr int SM100_MAXG = 8;
+constexpr int SM100_THREADS = 192;
+constexpr int BM = 128, BN = 128;
+
+struct Sm100Maps {
+    CUtensorMap q[SM100_MAXG];
+    CUtensorMap k[SM100_MAXG];
+    CUtensorMap v[SM100_MAXG];
+};
+struct Sm100Params {
+    float* o[SM100_MAXG];
+    float* lse[SM100_MAXG];
+    int H, N, d;
+    float scale2;  // scale * log2(e)
+};
+
+// ---- PTX wrappers --------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 lanes x 32 consecutive 32-bit columns: thread i of the warp receives lane (32*(warp%4) + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,"
+        "%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]),
+        "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]),
+        "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;   // version = 1 (Blackwell)
+    d |= (uint64_t)2 << 61;   // layout_type = SWIZZLE_128B
+    return d;
+}
+// instruction descriptor, kind::f16: bf16 x bf16 -> fp32 (cute::UMMA::InstrDescriptor bit layout)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) /*c=f32*/ | (1u << 7) /*a=bf16*/ | (1u << 10) /*b=bf16*/ | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// D = head_dim (40 or 80).  KB = number of 64-wide (128-byte) column blocks per operand row; KSTEPS = ceil(D/16); DV = O columns.
+template <int D>
+__global__ void __launch_bounds__(SM100_THREADS, (D <= 64) ? 2 : 1)
+attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params p) {
+    constexpr int KB = (D + 63) / 64;
+    constexpr int KSTEPS = (D + 15) / 16;
+    constexpr int DV = KSTEPS * 16;                 // 48 / 80: UMMA N (multiple of 16 at M = 128)
+    constexpr int TILE_BYTES = 128 * 128;           // one [128 rows][64 bf16] swizzled block
+    constexpr int OP_BYTES = KB * TILE_BYTES;       // one operand tile (Q, K or V)
+    constexpr int TMEM_COLS = (192 + DV <= 256) ? 256 : 512;
+    constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
+    constexpr int NSTAGE = 2;
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sQ = smem;
+    unsigned char* sK = sQ + OP_BYTES;
+    unsigned char* sV = sK + NSTAGE * OP_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTAGE * OP_BYTES);
+    uint64_t* q_full = bars + 0;
+    uint64_t* k_full = bars + 1;    // [2]
+    uint64_t* k_empty = bars + 3;   // [2]
+    uint64_t* v_full = bars + 5;    // [2]
+    uint64_t* v_empty = bars + 7;   // [2]
+    uint64_t* s_full = bars + 9;
+    uint64_t* s_free = bars + 10;
+    uint64_t* p_full = bars + 11;
+    uint64_t* pv_done = bars + 12;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
+    const int N = p.N;
+    const int nT = N / BN;
+    const int row_base = h * N;     // row offset of this head inside the (H*N, d) view
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+        mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 4 && lane == 0) { tma_prefetch_desc(&maps.q[g]); tma_prefetch_desc(&maps.k[g]); tma_prefetch_desc(&maps.v[g]); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(q_full, OP_BYTES);
+#pragma unroll
+            for (int b = 0; b < KB; ++b) tma_load_2d(sQ + b * TILE_BYTES, &maps.q[g], q_full, b * 64, row_base + q0);
+            for (int j = 0; j < nT; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(k_empty + s, ph ^ 1);
+                mbar_expect_tx(k_full + s, OP_BYTES);
+#pragma unroll
+                for (int b = 0; b < KB; ++b) tma_load_2d(sK + s * OP_BYTES + b * TILE_BYTES, &maps.k[g], k_full + s, b * 64, row_base + j * BN);
+                mbar_wait(v_empty + s, ph ^ 1);
+                mbar_expect_tx(v_full + s, OP_BYTES);
+#pragma unroll
+                for (int b = 0; b < KB; ++b) tma_load_2d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v[g], v_full + s, b * 64, row_base + j * BN);
+            }
+        }
+    } else if (warp == 5) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t IDESC_QK = make_idesc(BM, BN, 0, 0);
+            constexpr uint32_t IDESC_PV = make_idesc(BM, DV, 0, 1);
+            const uint32_t aQ = smem_addr(sQ);
+            auto issue_qk = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(k_full + s, (j >> 1) & 1);
+                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                tc_fence_after();
+                const uint32_t aK = smem_addr(sK + s * OP_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks) {
+                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 64-wide block, then 32 B per 16 elements
+                    umma_ss(tmem + COL_S, make_desc(aQ + off, 16, 1024), make_desc(aK + off, 16, 1024), IDESC_QK, ks > 0);
+                }
+                tc_commit(s_full);        // S(j) complete -> softmax
+                tc_commit(k_empty + s);   // K stage reusable
+            };
+            mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < nT; ++j) {
+                if (j + 1 < nT) issue_qk(j + 1);
+                const int s = j & 1;
+                mbar_wait(v_full + s, (j >> 1) & 1);
+                mbar_wait(p_full, j & 1);
+                tc_fence_after();
+                const uint32_t aV = smem_addr(sV + s * OP_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BN / 16; ++kk) {
+                    // V tile rows = keys (the MMA K dimension), MN-major: 16 keys = 16 rows x 128 B; LBO = next 64-wide column block
+                    umma_ts(tmem + COL_O, tmem + COL_P + kk * 8, make_desc(aV + kk * 2048, TILE_BYTES, 1024), IDESC_PV, (j > 0 || kk > 0));
+                }
+                tc_commit(pv_done);
+                tc_commit(v_empty + s);
+            }
+        }
+    } else {
+        // ================= softmax / correction / epilogue (warps 0-3) =================
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const float scale2 = p.scale2;
+        float m_run = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < nT; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t sr[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_off + COL_S + c * 32, sr + c * 32);
+            tmem_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(s_free);      // S(j) is in registers: QK^T(j+1) may overwrite it
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+            const float m_cand = fmaxf(m_run, mx * scale2);
+            const bool grow = (m_cand - m_run) > 8.0f;           // lazy rescale: tolerate up to 2^8 headroom
+            const float m_new = grow ? m_cand : m_run;
+            const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
+            m_run = m_new;
+            float rs = 0.f;
+            uint32_t pk[64];
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+                const float p0 = ex2(fmaf(__uint_as_float(sr[2 * c]), scale2, -m_new));
+                const float p1 = ex2(fmaf(__uint_as_float(sr[2 * c + 1]), scale2, -m_new));
+                rs += p0 + p1;
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+                pk[c] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            l_run = l_run * alpha + rs;
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);                 // PV(j-1) has finished reading P and updating O
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll
+                    for (int c = 0; c < DV / 16; ++c) {
+                        uint32_t orr[16];
+                        tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
+                        tmem_st16(tmem + lane_off + COL_O + c * 16, orr);
+                    }
+                }
+            }
+            tmem_st32(tmem + lane_off + COL_P, pk);
+            tmem_st32(tmem + lane_off + COL_P + 32, pk + 32);
+            tmem_wait_st();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        // epilogue: O / l -> global fp32, lse
+        mbar_wait(pv_done, (nT - 1) & 1);
+        tc_fence_after();
+        const int row = q0 + warp * 32 + lane;
+        const float inv = 1.0f / l_run;
+        float* og = p.o[g] + ((long)h * N + row) * D;
+#pragma unroll
+        for (int c = 0; c < DV / 16; ++c) {
+            uint32_t orr[16];
+            tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 16; e += 4) {
+                if (c * 16 + e < D)
+                    *reinterpret_cast<float4*>(og + c * 16 + e) = make_float4(__uint_as_float(orr[e]) * inv, __uint_as_float(orr[e + 1]) * inv,
+                                                                             __uint_as_float(orr[e + 2]) * inv, __uint_as_float(orr[e + 3]) * inv);
+            }
+        }
+        p.lse[g][(long)h * N + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+// (rows, d) bf16 row-major viewed as a 2-D tensor; box = 64 columns (128 B, zero-filled past d) x 128 rows, SWIZZLE_128B
+static int make_map(CUtensorMap* m, const void* base, long rows, int d) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)d * sizeof(bf16)};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return GD_OK;
+}
+
+template <int D> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
+    constexpr int KB = (D + 63) / 64;
+    const size_t smem = (size_t)5 * KB * 128 * 128 + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid(p.N / BM, p.H, G);
+    attn_fwd_sm100_kernel<D><<<grid, SM100_THREADS, smem, st>>>(maps, p);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
+}  // namespace gd
+
+using namespace gd;
+
+extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, const void* const* v, void* const* o, void* const* lse, int G, int H,
+                                 int N, int Nk, int d, float scale, void* stream) {
+    GD_CHECK_ARG(q && k && v && o && lse && G > 0 && G <= SM100_MAXG && H > 0);
+    if (!(N == Nk && N % 128 == 0 && (d == 40 || d == 80)))
+        return set_error(GD_ERR_UNSUPPORTED, "gd_attn_fwd_sm100 serves N == Nk, N %% 128 == 0, d in {40, 80}; got N=%d Nk=%d d=%d", N, Nk, d);
+    Sm100Maps maps;
+    Sm100Params p;
+    for (int g = 0; g < G; ++g) {
+        GD_CHECK_ARG(q[g] && k[g] && v[g] && o[g] && lse[g]);
+        int rc;
+        if ((rc = make_map(&maps.q[g], q[g], (long)H * N, d)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.k[g], k[g], (long)H * N, d)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.v[g], v[g], (long)H * N, d)) != GD_OK) return rc;
+        p.o[g] = (float*)o[g];
+        p.lse[g] = (float*)lse[g];
+    }
+    p.H = H; p.N = N; p.d = d; p.scale2 = scale * 1.4426950408889634f;
+    if (d == 40) return launch_sm100<40>(maps, p, G, (cudaStream_t)stream);
+    return launch_sm100<80>(maps, p, G, (cudaStream_t)stream);
+}
