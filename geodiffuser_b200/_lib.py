@@ -44,7 +44,8 @@ SIGNATURES = {
 
 _LIB = None
 HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
-LAUNCHES = 0  # kernels-launching C-ABI calls made by this process (bench.py reports it)
+LAUNCHES = 0  # CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
+KERNELS_PER_CALL = {"gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2}  # every other entry point launches one
 
 
 class GeoDiffuserB200Error(RuntimeError):
@@ -70,11 +71,37 @@ def lib():
     return _LIB
 
 
-def call(name, *args):
+PROFILE = None  # bench.py sets this to {} to time selected entry points with CUDA events on the launching (current) stream
+
+
+def profile_begin(names):
+    """start collecting (start, end) CUDA-event pairs for the named entry points; meta() may tag each call (e.g. with its FLOPs)"""
+    global PROFILE
+    PROFILE = {"names": set(names), "events": []}
+
+
+def profile_end():
+    """-> {name: [(milliseconds, tag), ...]} ; call after torch.cuda.synchronize()"""
+    global PROFILE
+    out = {}
+    for name, tag, e0, e1 in PROFILE["events"]:
+        out.setdefault(name, []).append((e0.elapsed_time(e1), tag))
+    PROFILE = None
+    return out
+
+
+def call(name, *args, tag=None):
     global LAUNCHES
     L_ = lib()
-    rc = getattr(L_, name)(*args)
-    LAUNCHES += 1
+    if PROFILE is not None and name in PROFILE["names"]:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(L_, name)(*args)
+        e1.record()
+        PROFILE["events"].append((name, tag, e0, e1))
+    else:
+        rc = getattr(L_, name)(*args)
+    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise GeoDiffuserB200Error(f"{name} failed with status {rc}: {L_.gd_last_error().decode()}")
 

@@ -184,21 +184,31 @@ def synthetic_embeddings(seed=SEED, device="cuda"):
     return text.to(device), uncond.to(device), x0.to(device)
 
 
-def perform_geometric_edit(model, kind="rotate3d", num_ddim_steps=NUM_DDIM_STEPS, perform_ddim_inversion=True, seed=SEED, return_log=False,
-                           **overrides):
-    """editor.py:428-711 on synthetic inputs: correspondence field -> (DDIM inversion) -> controller -> edit loop.
-    kind in synth.EDIT_KINDS; returns the final (2,4,64,64) latents [reference, edited]."""
+def stage_inputs(depth, image_mask, text_embeddings, uncond_embeddings, x0, device):
+    """Host -> device copies of one edit request (the only H2D traffic of an edit).  Returns (staged dict, bytes copied)."""
+    d_dev, m_dev = geometry.stage_depth_mask(depth, image_mask, device)
+    obj = torch.from_numpy(np.ascontiguousarray(image_mask, dtype=np.float32)).to(device, non_blocking=True)
+    text = text_embeddings.to(device, non_blocking=True).float()
+    uncond = uncond_embeddings.to(device, non_blocking=True).float()
+    x0 = x0.to(device, non_blocking=True).float()
+    staged = dict(depth=d_dev, mask=m_dev, obj_mask=obj, text=text, uncond=uncond, x0=x0)
+    nbytes = sum(t.numel() * t.element_size() for t in staged.values())
+    return staged, nbytes
+
+
+def run_edit(model, staged, transform_in, edit_type="geometry_editor", num_ddim_steps=50, perform_ddim_inversion=True, seed=SEED,
+             return_log=False, **overrides):
+    """editor.py:428-711 on device-resident inputs: correspondence field -> DDIM inversion -> controller -> edit loop.
+    Returns the final (2,4,64,64) latents [reference, edited] on the device."""
     global NUM_DDIM_STEPS
     NUM_DDIM_STEPS = num_ddim_steps
     device = model.device
-    edit_type = "geometry_remover" if kind == "remove" else "geometry_editor"
     hp = dict(EXP_PARAMS[edit_type])
     hp.update(overrides)
-    image, depth, mask, T = synth.edit_inputs(kind)
-    t_coords, _, amodal = geometry.get_transform_coordinates(image / 255.0, depth, mask, T, return_mesh=True, device=device)
-    g = geometry.get_transform_coordinates.last
+    g = geometry.correspondence_field_device(staged["depth"], staged["mask"], transform_in)
+    mesh = geometry.mesh_mask(g["coords"], g["mask"])
     transform_coordinates = g["coords"][None]  # stays on the device (the reference round-trips through numpy, editor.py:546-547)
-    text, uncond, x0 = synthetic_embeddings(seed, device)
+    text, uncond, x0 = staged["text"], staged["uncond"], staged["x0"]
     model.scheduler.set_timesteps(num_ddim_steps)
     if perform_ddim_inversion:
         ddim_latents = ddim_inversion_loop(model, x0, torch.cat([uncond[:1], text[:1]]), hp["guidance_scale"], num_ddim_steps)
@@ -208,8 +218,9 @@ def perform_geometric_edit(model, kind="rotate3d", num_ddim_steps=NUM_DDIM_STEPS
     x_t = ddim_latents[-1]
     cls = AttentionGeometryRemover if edit_type == "geometry_remover" else AttentionGeometryEdit
     controller = cls(["", ""], num_ddim_steps, cross_replace_steps=hp["cross_replace_steps"], self_replace_steps=hp["self_replace_steps"],
-                     image_mask=mask.astype(np.float32), empty_scale=0.0, use_all=False, obj_edit_step=hp["obj_edit_step"], device=device)
-    controller.amodal_mask = geometry.torch_erode(g["mesh_mask"][None, None])  # editor.py:633
+                     image_mask=None, empty_scale=0.0, use_all=False, obj_edit_step=hp["obj_edit_step"], device=device)
+    controller.image_mask = staged["obj_mask"][None].tile(2, 1, 1)
+    controller.amodal_mask = geometry.torch_erode(mesh[None, None])  # editor.py:633
     if hp.get("loss_weights_dict") is not None:
         import copy
         lw = copy.deepcopy(hp["loss_weights_dict"])
@@ -217,11 +228,38 @@ def perform_geometric_edit(model, kind="rotate3d", num_ddim_steps=NUM_DDIM_STEPS
         controller.default_loss_weights = lw  # aliased exactly like editor.py:637-638
     latents, _, log = text2image_ldm_stable(
         model, ["", ""], controller, num_inference_steps=num_ddim_steps, guidance_scale=hp["guidance_scale"], latent=x_t,
-        uncond_embeddings=uncond, text_embeddings=text, transform_coordinates=transform_coordinates,
-        mask_obj=torch.from_numpy(mask.astype(np.float32))[None, None], optimize_steps=hp["optimize_steps"], latent_replace=hp["latent_replace"],
-        lr=hp["lr"], optimize_embeddings=hp["optimize_embeddings"], optimize_latents=hp["optimize_latents"], ddim_latents=ddim_latents,
-        edit_type=edit_type, skip_optim_steps=hp["skip_optim_steps"], removal_loss_value_in=hp.get("removal_loss_value_in", -1.5))
+        uncond_embeddings=uncond, text_embeddings=text, transform_coordinates=transform_coordinates, mask_obj=staged["obj_mask"],
+        optimize_steps=hp["optimize_steps"], latent_replace=hp["latent_replace"], lr=hp["lr"], optimize_embeddings=hp["optimize_embeddings"],
+        optimize_latents=hp["optimize_latents"], ddim_latents=ddim_latents, edit_type=edit_type, skip_optim_steps=hp["skip_optim_steps"],
+        removal_loss_value_in=hp.get("removal_loss_value_in", -1.5))
     model.unet.set_attn_processor(VanillaAttentionProcessor())  # editor.py:698
     if return_log:
         return latents, log
     return latents
+
+
+def perform_geometric_edit(model, depth, image_mask, transform_in, text_embeddings, uncond_embeddings, x0, edit_type="geometry_editor",
+                           **kw):
+    """Public entry for one edit request with HOST inputs (numpy depth / mask, host tensors for the embeddings and the image latent):
+    host->device staging, the edit, and the device->host copy of the result.  Returns (latents on the host, h2d bytes, d2h bytes)."""
+    staged, h2d = stage_inputs(depth, image_mask, text_embeddings, uncond_embeddings, x0, model.device)
+    latents = run_edit(model, staged, transform_in, edit_type, **kw)
+    out = latents.cpu()
+    return out, h2d, out.numel() * out.element_size()
+
+
+def synthetic_request(kind="rotate3d", seed=SEED, pin=True):
+    """host-side inputs of one synthetic edit request"""
+    image, depth, mask, T = synth.edit_inputs(kind)
+    text, uncond, x0 = synthetic_embeddings(seed, "cpu")
+    if pin and torch.cuda.is_available():
+        text, uncond, x0 = text.pin_memory(), uncond.pin_memory(), x0.pin_memory()
+    edit_type = "geometry_remover" if kind == "remove" else "geometry_editor"
+    return dict(depth=depth, image_mask=mask, transform_in=T, text_embeddings=text, uncond_embeddings=uncond, x0=x0, edit_type=edit_type)
+
+
+def perform_synthetic_edit(model, kind="rotate3d", num_ddim_steps=NUM_DDIM_STEPS, return_log=False, **kw):
+    """convenience wrapper used by the tests: device-side result of one synthetic edit"""
+    req = synthetic_request(kind, pin=False)
+    staged, _ = stage_inputs(req["depth"], req["image_mask"], req["text_embeddings"], req["uncond_embeddings"], req["x0"], model.device)
+    return run_edit(model, staged, req["transform_in"], req["edit_type"], num_ddim_steps=num_ddim_steps, return_log=return_log, **kw)

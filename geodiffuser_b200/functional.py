@@ -85,7 +85,7 @@ def attention_forward(qs, ks, vs, scale):
     if _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024:
         entry = "gd_attn_fwd_sm100"
     call(entry, _lib.ptr_array(qs), _lib.ptr_array(ks), _lib.ptr_array(vs), _lib.ptr_array([O[g] for g in range(G)]),
-         _lib.ptr_array([LSE[g] for g in range(G)]), G, H, N, Nk, d, float(scale), stream())
+         _lib.ptr_array([LSE[g] for g in range(G)]), G, H, N, Nk, d, float(scale), stream(), tag=(G, H, N, Nk, d))
     return O, LSE
 
 

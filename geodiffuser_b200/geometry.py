@@ -57,22 +57,26 @@ def normalise_depth(depth):
     return depth
 
 
-def correspondence_field(depth, obj_mask, transform_in, focal_length=FOCAL_LENGTH, device=None):
-    """A1: depth (H,W) numpy, obj_mask (H,W) or None, transform_in (4,4) -> dict with CUDA tensors
-    coords (H,W,3) f32 = (x_norm, y_norm, Z), mask (H,W) f32, cam (3,H,W), centre (3,), Tc (4,4 host tensor).
-    The 4x4 conjugation T' = C^-1 T C is done with torch on the host like the reference (warp_utils.py:431-437);
-    everything per-pixel runs in csrc/geometry.cu."""
+def stage_depth_mask(depth, obj_mask, device=None):
+    """Host part of A1 (vis_utils.py:408-425: float64 numpy depth normalisation and mask threshold, as the reference) followed by
+    the host->device copy of the two (H,W) fp32 planes.  Returns (depth_dev, mask_dev)."""
     dev = _dev(device)
     d64 = normalise_depth(depth)
     m = (d64 < 0.95) * 1.0
     if obj_mask is not None:
         m = np.asarray(obj_mask, dtype=np.float64) * m
     mask = ((torch.tensor(m)[None, None] >= 0.5) * 1.0)[0, 0].float()
-    H, W = d64.shape
+    return torch.from_numpy(d64).float().to(dev).contiguous(), mask.to(dev).contiguous()
+
+
+def correspondence_field_device(d_dev, mask_dev, transform_in, focal_length=FOCAL_LENGTH):
+    """A1 on device-resident inputs: d_dev, mask_dev (H,W) fp32 CUDA -> dict with coords (H,W,3) f32 = (x_norm, y_norm, Z), cam (3,H,W),
+    centre (3,), Tc (4,4 host).  The 4x4 conjugation T' = C^-1 T C is done with torch on the host like the reference
+    (warp_utils.py:431-437, 12-byte D2H of the centroid); everything per-pixel runs in csrc/geometry.cu."""
+    dev = d_dev.device
+    H, W = d_dev.shape
     K = torch.from_numpy(camera_matrix(focal_length, focal_length, W / 2.0, H / 2.0))[None].float()
     Kinv = K.inverse()[0].contiguous()
-    d_dev = torch.from_numpy(d64).float().to(dev).contiguous()
-    mask_dev = mask.to(dev).contiguous()
     cam = torch.empty(3, H, W, device=dev, dtype=torch.float32)
     centre4 = torch.empty(4, device=dev, dtype=torch.float32)
     call("gd_corr_pixel2cam", ptr(d_dev), ptr(mask_dev), H, W, _lib.host_f32(Kinv.reshape(-1).tolist()), ptr(cam), ptr(centre4), stream())
@@ -81,11 +85,17 @@ def correspondence_field(depth, obj_mask, transform_in, focal_length=FOCAL_LENGT
     C[:3, 3] += -centre
     C = C[None]
     T = transform_in if torch.is_tensor(transform_in) else torch.tensor(np.asarray(transform_in))
-    Tc = (C.inverse() @ T[None].float() @ C).float()[0]
+    Tc = (C.inverse() @ T.cpu()[None].float() @ C).float()[0]
     coords = torch.empty(H, W, 3, device=dev, dtype=torch.float32)
     call("gd_corr_project", ptr(cam), H, W, _lib.host_f32(Tc[:3, :].reshape(-1).tolist()), _lib.host_f32(K[0].reshape(-1).tolist()),
          ptr(coords), stream())
     return dict(coords=coords, mask=mask_dev, cam=cam, centre=centre, Tc=Tc, depth=d_dev)
+
+
+def correspondence_field(depth, obj_mask, transform_in, focal_length=FOCAL_LENGTH, device=None):
+    """A1 from host inputs: depth (H,W) numpy, obj_mask (H,W) or None, transform_in (4,4)."""
+    d_dev, mask_dev = stage_depth_mask(depth, obj_mask, device)
+    return correspondence_field_device(d_dev, mask_dev, transform_in, focal_length)
 
 
 def mesh_mask(coords, mask):

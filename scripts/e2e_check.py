@@ -13,7 +13,7 @@ torch.cuda.synchronize()
 print("model built", time.time() - t0, flush=True)
 for it in range(2):
     torch.cuda.synchronize(); t0 = time.time(); l0 = _lib.LAUNCHES
-    lat, log = editor.perform_geometric_edit(model, kind, num_ddim_steps=steps, return_log=True)
+    lat, log = editor.perform_synthetic_edit(model, kind, num_ddim_steps=steps, return_log=True)
     torch.cuda.synchronize()
     print(f"edit {it}: {time.time()-t0:.2f}s launches={_lib.LAUNCHES-l0} finite={bool(torch.isfinite(lat).all())} norm={float(lat[-1].norm()):.3f}", flush=True)
     for i in sorted(log)[:3]:
