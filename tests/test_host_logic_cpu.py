@@ -1,0 +1,89 @@
+"""Host-side mirror of the reference interface: controller state machine, loss-weight aliasing, adaptive schedule, scheduler tables,
+processor registration.  No CUDA needed."""
+import numpy as np
+import pytest
+import torch
+
+from geodiffuser_b200 import attention_processors as AP
+from geodiffuser_b200 import diffusion, optimization, unet_sd15
+
+
+def make(kind="edit"):
+    cls = AP.AttentionGeometryEdit if kind == "edit" else AP.AttentionGeometryRemover
+    return cls(["", ""], 50, cross_replace_steps={"default_": 0.95}, self_replace_steps=0.95, image_mask=np.zeros((512, 512), np.float32),
+               empty_scale=0.0, use_all=False, obj_edit_step=0.9, device="cpu")
+
+
+def test_controller_attributes_match_reference_contract():
+    c = make()
+    for attr in ("loss", "loss_log_dict", "loss_weight_dict", "mask_new_warped", "cur_step", "amodal_mask", "image_mask", "store_attention_maps",
+                 "attention_store", "coords_base", "coords_edit", "use_cfg", "num_self_replace", "masks_cache_dict", "batch_size"):
+        assert hasattr(c, attr), attr
+    assert c.num_self_replace == (0, 47) and c.image_mask.shape == (2, 512, 512)
+    assert set(c.loss_log_dict["self"]) == {"sim", "movement", "removal", "smoothness"}       # no `amodal` key (reference :626-630)
+    assert set(make("remove").loss_log_dict["cross"]) == {"sim", "removal", "smoothness"}
+    assert c.default_loss_weights["self"]["removal"] == 1.67 and make("remove").default_loss_weights["self"]["removal"] == 3.6
+
+
+def test_loss_weight_aliasing_quirk():
+    """initialize_default_loss_weights() re-binds the SAME dict, so the adaptive schedule's reset is a no-op"""
+    c = make()
+    c.loss_weight_dict["self"]["removal"] *= 1.3
+    c.initialize_default_loss_weights()
+    assert abs(c.loss_weight_dict["self"]["removal"] - 1.67 * 1.3) < 1e-9
+
+
+def test_adaptive_schedule():
+    c = make()
+    w0 = c.loss_weight_dict["self"]["removal"]
+    log = {"self": {"removal": 0.0}}
+    optimization.adaptive_optimization_step_editing(c, 0, 2, log, num_ddim_steps=50, removal_loss_value_in=-1.5)   # expected < current -> x1.3
+    assert abs(c.loss_weight_dict["self"]["removal"] - w0 * 1.3) < 1e-9
+    log = {"self": {"removal": -5.0}}
+    optimization.adaptive_optimization_step_editing(c, 0, 2, log, num_ddim_steps=50, removal_loss_value_in=-1.5)   # far below -> /2
+    assert abs(c.loss_weight_dict["self"]["removal"] - w0 * 1.3 / 2.0) < 1e-9
+    r = make("remove")
+    w0 = r.loss_weight_dict["self"]["removal"]
+    optimization.adaptive_optimization_step_remover(r, 0, 2, log, num_ddim_steps=50, removal_loss_value_in=-1.5)
+    assert abs(r.loss_weight_dict["self"]["removal"] - w0 / 2.5) < 1e-9
+    optimization.adaptive_optimization_step_remover(r, 25, 2, {"self": {"removal": 0.0}}, num_ddim_steps=50)       # 0.4 < frac < 0.8 -> x2
+    assert abs(r.loss_weight_dict["self"]["removal"] - w0 / 2.5 * 2.0) < 1e-9
+
+
+def test_scheduler_tables():
+    s = diffusion.DDIMScheduler()
+    s.set_timesteps(50)
+    assert s.timesteps.tolist()[:3] == [980, 960, 940] and s.timesteps.tolist()[-1] == 0
+    c1, c2, c3, c4 = s._coefficients(0)
+    a0 = float(s.alphas_cumprod[0])
+    assert abs(c3 - a0 ** 0.5) < 1e-6            # set_alpha_to_one=False: final alpha = alphas_cumprod[0]
+    i1, i2, i3, i4 = s.inverse_coefficients(0)
+    assert i1 == 0.0 and i2 == 1.0               # DDIMInverseScheduler: alpha before the first step is 1
+
+
+def test_registration_and_mode_switch():
+    model = unet_sd15.build_model("cpu", tiny=True)
+    c = make()
+    tc = torch.zeros(1, 512, 512, 3)
+    AP.register_attention_control_diffusers(model, c, tc)
+    procs = model.unet.attn_processors
+    assert len(procs) == 32 and c.num_att_layers == 32
+    assert all(isinstance(p, AP.EditProcessor) for p in procs.values())
+    places = {k.split(".")[0]: p.place_in_unet for k, p in procs.items()}
+    assert places == {"down_blocks": "down", "mid_block": "mid", "up_blocks": "up"}
+    AP.set_attn_processor_for_edit(model, coords_base=(0, 1), coords_edit=(1, 2), use_cfg=False)
+    assert (c.coords_base, c.coords_edit, c.use_cfg) == ((0, 1), (1, 2), False)
+    model.unet.set_attn_processor(AP.VanillaAttentionProcessor())
+    assert all(isinstance(p, AP.VanillaAttentionProcessor) for p in model.unet.attn_processors.values())
+    with pytest.raises(ValueError):
+        model.unet.set_attn_processor({"x": None})
+
+
+def test_unet_topology_is_sd15():
+    import torch.nn as nn
+
+    with torch.device("meta"):
+        u = unet_sd15.UNet2DConditionModel()
+    assert sum(p.numel() for p in u.parameters()) == 859520964    # SD-1.x UNet parameter count
+    heads = {m.to_q.in_features // m.heads for _, m in u._attention_modules()}
+    assert heads == {40, 80, 160}

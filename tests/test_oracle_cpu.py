@@ -1,0 +1,60 @@
+"""The CPU oracle (test infrastructure) against the golden vectors that oracle/make_golden.py produced from the reference itself.
+Sized to run in well under a minute."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, relerr
+from geodiffuser_b200 import synth
+from oracle import geodiff_oracle as O
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+@pytest.mark.parametrize("kind", ["translate2d", "rotate3d", "remove"])
+def test_oracle_geometry_vs_golden(kind):
+    z = np.load(os.path.join(GOLDEN, f"geometry_{kind}.npz"))
+    image, depth, mask, T = synth.edit_inputs(kind)
+    g = O.corr_build(depth.copy(), mask.copy(), T)
+    assert sha(g["coords"]) == str(z["coords512_sha"])
+    for S in (16, 8):
+        cS = z[f"coords{S}"]
+        idx, _, d2 = O.splat_index(cS[None])
+        np.testing.assert_array_equal(idx[0], z[f"idx{S}"])
+        np.testing.assert_array_equal(d2[0], z[f"dist2_{S}"])
+    amodal = O.erode3(O.mesh_mask(g["coords"], g["mask"]))
+    assert sha(amodal) == str(z["amodal512_sha"])
+
+
+def test_oracle_attention_layer_vs_golden():
+    """edit_cross_S16_cfg: forward-only case small enough for the CPU suite"""
+    z = np.load(os.path.join(GOLDEN, "attn_edit_cross_S16_cfg.npz"))
+    zg = np.load(os.path.join(GOLDEN, "geometry_translate2d.npz"))
+    S, H, d = 16, 2, 32
+    masks = {k: zg[f"{k}{S}"] for k in ("mask_new_warped", "mask_warp", "amodal_mask", "mask_intersection", "mask_1_empty", "mask_wo_edit")}
+    q, k, v = (torch.from_numpy(a) for a in synth.qkv(106, 4, H, S * S, 77, d))
+    with torch.no_grad():
+        res = O.edit_layer(q, k, v, True, d ** -0.5, H, (2, 3), (3, 4), masks, zg[f"coords{S}"], True, True)
+    assert relerr(res["out"].numpy(), z["out"]) <= 2e-5
+
+
+def test_oracle_elementwise_vs_golden():
+    z = np.load(os.path.join(GOLDEN, "elementwise.npz"))
+    lat, ctx = torch.from_numpy(z["lat"]), torch.from_numpy(z["ctx"])
+    nl, nc = O.update_latent(lat, torch.from_numpy(z["w1"]), 0.3, z["mask512"], ctx, 0.5 * torch.from_numpy(z["w2"]))
+    assert relerr(nl.numpy(), z["new_lat"]) <= 1e-6 and relerr(nc.numpy(), z["new_ctx"]) <= 1e-6
+    al = O.ddim_alphas()
+    np.testing.assert_allclose(al.numpy(), z["alphas"], rtol=1e-6)
+    assert relerr(O.ddim_step(lat, torch.from_numpy(z["eps"]), 980, al).numpy(), z["ddim_980"]) <= 1e-6
+
+
+def test_loop_golden_is_pinned_to_reference():
+    for kind in ("translate2d", "rotate3d", "remove"):
+        z = np.load(os.path.join(GOLDEN, f"loop_{kind}_tiny.npz"))
+        assert float(z["pin_err_vs_reference"]) <= 1e-2
+        assert np.isfinite(z["latents"]).all()
