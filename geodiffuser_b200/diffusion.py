@@ -10,6 +10,19 @@ from ._lib import call, ptr, stream
 AUTOCAST_DTYPE = torch.bfloat16  # the reference autocasts to fp16 (diffusion.py:39); BASELINE.json names BF16 for this build
 
 
+def set_body_dtype(dtype):
+    """dtype the UNet body (the caller of the path: convolutions, projections, norms) runs in.  torch.bfloat16 is the product setting;
+    torch.float32 takes the caller's rounding out of a parity run so that the only reduced-precision arithmetic left is the path's own
+    BF16 kernels (tests/test_loop_gpu.py)."""
+    global AUTOCAST_DTYPE
+    assert dtype in (torch.bfloat16, torch.float32)
+    AUTOCAST_DTYPE = dtype
+
+
+def body_autocast():
+    return torch.autocast("cuda", dtype=torch.bfloat16, enabled=AUTOCAST_DTYPE == torch.bfloat16)
+
+
 class DDIMScheduler:
     def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012):
         betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
@@ -75,7 +88,7 @@ def diffusion_step(model, controller, latents, context, t, guidance_scale, low_r
                    return_noise=False):
     """diffusion.py:40-59.  With use_cfg=False the UNet runs under autograd (the caller enables grad) and the returned noise carries
     the graph; the latent step itself is never differentiated by the reference loop (only controller.loss is, editor.py:273)."""
-    with torch.autocast("cuda", dtype=AUTOCAST_DTYPE):
+    with body_autocast():
         if use_cfg:
             latents_input = torch.cat([latents] * 2)
             noise_pred = model.unet(latents_input, t, encoder_hidden_states=context)["sample"]

@@ -12,7 +12,7 @@ import torch
 from . import geometry, synth
 from .attention_processors import (AttentionGeometryEdit, AttentionGeometryRemover, VanillaAttentionProcessor,
                                    register_attention_control_diffusers, set_attn_processor_for_edit)
-from .diffusion import AUTOCAST_DTYPE, diffusion_step
+from .diffusion import body_autocast, diffusion_step
 from .optimization import (_update_latent, adaptive_optimization_step_editing, adaptive_optimization_step_remover, norm_tensor,
                            rescale_to_norm_)
 from ._lib import call, ptr, stream
@@ -51,7 +51,7 @@ def ddim_inversion_loop(model, latent, context, guidance_scale=3.0, num_ddim_ste
     all_latent = [latent]
     latents = latent.clone().detach().float()
     for t in reversed(sched.timesteps.tolist()):  # 0, 20, ..., 980 (DDIMInverseScheduler, leading spacing)
-        with torch.autocast("cuda", dtype=AUTOCAST_DTYPE):
+        with body_autocast():
             noise_pred = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
         eu, ec = noise_pred.chunk(2)
         latents = sched.next_step_cfg(eu, ec, guidance_scale, t, latents)
@@ -196,26 +196,12 @@ def stage_inputs(depth, image_mask, text_embeddings, uncond_embeddings, x0, devi
     return staged, nbytes
 
 
-def run_edit(model, staged, transform_in, edit_type="geometry_editor", num_ddim_steps=50, perform_ddim_inversion=True, seed=SEED,
-             return_log=False, **overrides):
-    """editor.py:428-711 on device-resident inputs: correspondence field -> DDIM inversion -> controller -> edit loop.
-    Returns the final (2,4,64,64) latents [reference, edited] on the device."""
-    global NUM_DDIM_STEPS
-    NUM_DDIM_STEPS = num_ddim_steps
+def make_controller(model, staged, transform_in, edit_type, hp, num_ddim_steps=50):
+    """editor.py:508-638: correspondence field, amodal mesh mask and the controller of one edit.  Returns (controller, transform_coordinates)."""
     device = model.device
-    hp = dict(EXP_PARAMS[edit_type])
-    hp.update(overrides)
     g = geometry.correspondence_field_device(staged["depth"], staged["mask"], transform_in)
     mesh = geometry.mesh_mask(g["coords"], g["mask"])
     transform_coordinates = g["coords"][None]  # stays on the device (the reference round-trips through numpy, editor.py:546-547)
-    text, uncond, x0 = staged["text"], staged["uncond"], staged["x0"]
-    model.scheduler.set_timesteps(num_ddim_steps)
-    if perform_ddim_inversion:
-        ddim_latents = ddim_inversion_loop(model, x0, torch.cat([uncond[:1], text[:1]]), hp["guidance_scale"], num_ddim_steps)
-    else:
-        gen = torch.Generator().manual_seed(seed + 2)
-        ddim_latents = [x0] + [torch.randn(1, 4, 64, 64, generator=gen).to(device) for _ in range(num_ddim_steps)]
-    x_t = ddim_latents[-1]
     cls = AttentionGeometryRemover if edit_type == "geometry_remover" else AttentionGeometryEdit
     controller = cls(["", ""], num_ddim_steps, cross_replace_steps=hp["cross_replace_steps"], self_replace_steps=hp["self_replace_steps"],
                      image_mask=None, empty_scale=0.0, use_all=False, obj_edit_step=hp["obj_edit_step"], device=device)
@@ -226,6 +212,27 @@ def run_edit(model, staged, transform_in, edit_type="geometry_editor", num_ddim_
         lw = copy.deepcopy(hp["loss_weights_dict"])
         controller.loss_weight_dict = lw
         controller.default_loss_weights = lw  # aliased exactly like editor.py:637-638
+    return controller, transform_coordinates
+
+
+def run_edit(model, staged, transform_in, edit_type="geometry_editor", num_ddim_steps=50, perform_ddim_inversion=True, seed=SEED,
+             return_log=False, **overrides):
+    """editor.py:428-711 on device-resident inputs: correspondence field -> DDIM inversion -> controller -> edit loop.
+    Returns the final (2,4,64,64) latents [reference, edited] on the device."""
+    global NUM_DDIM_STEPS
+    NUM_DDIM_STEPS = num_ddim_steps
+    device = model.device
+    hp = dict(EXP_PARAMS[edit_type])
+    hp.update(overrides)
+    controller, transform_coordinates = make_controller(model, staged, transform_in, edit_type, hp, num_ddim_steps)
+    text, uncond, x0 = staged["text"], staged["uncond"], staged["x0"]
+    model.scheduler.set_timesteps(num_ddim_steps)
+    if perform_ddim_inversion:
+        ddim_latents = ddim_inversion_loop(model, x0, torch.cat([uncond[:1], text[:1]]), hp["guidance_scale"], num_ddim_steps)
+    else:
+        gen = torch.Generator().manual_seed(seed + 2)
+        ddim_latents = [x0] + [torch.randn(1, 4, 64, 64, generator=gen).to(device) for _ in range(num_ddim_steps)]
+    x_t = ddim_latents[-1]
     latents, _, log = text2image_ldm_stable(
         model, ["", ""], controller, num_inference_steps=num_ddim_steps, guidance_scale=hp["guidance_scale"], latent=x_t,
         uncond_embeddings=uncond, text_embeddings=text, transform_coordinates=transform_coordinates, mask_obj=staged["obj_mask"],

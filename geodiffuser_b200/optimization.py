@@ -47,8 +47,12 @@ def _update_latent(latents, loss, step_size, mask=None, context=None, scaler=Non
     """optimization.py:165-253.  The torch.optim branch is dead in the reference (use_optimizer is never forwarded)."""
     if optimizer is not None or scaler is not None:
         raise NotImplementedError("only the optimizer=None branch is reachable from the reference drivers (editor.py:233-234)")
-    grads = torch.autograd.grad(loss, [latents, context], retain_graph=False)
-    return apply_latent_update(latents, grads[0], step_size, mask, context, grads[1])
+    # The fused layer returns no gradient (None) where the reference's graph carries a structural zero (base sample, detached K/V of
+    # the remover's cross layers), so an input the loss does not reach comes back undefined here instead of as zeros.
+    grads = torch.autograd.grad(loss, [latents, context], retain_graph=False, allow_unused=True)
+    g_lat = grads[0] if grads[0] is not None else torch.zeros_like(latents)
+    g_ctx = grads[1] if grads[1] is not None else torch.zeros_like(context)
+    return apply_latent_update(latents, g_lat, step_size, mask, context, g_ctx)
 
 
 def _adaptive(controller, i, skip_optim_steps, out_loss_log_dict, num_ddim_steps, removal_loss_value_in, reduce_div):

@@ -1,0 +1,117 @@
+"""Micro-benchmark + accuracy check of the attention kernels of the path at the shapes the edit loop launches (not a bench.py number;
+used to iterate on a kernel and as the short command for `ncu --set full`).
+
+    python scripts/bench_kernels.py [--iters 20] [--only fwd|bwd] [--quick]
+"""
+import sys
+
+import torch
+
+sys.path.insert(0, ".")
+from geodiffuser_b200 import _lib  # noqa: E402
+from geodiffuser_b200._lib import call, ptr, stream  # noqa: E402
+
+iters = int(sys.argv[sys.argv.index("--iters") + 1]) if "--iters" in sys.argv else 20
+only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None
+quick = "--quick" in sys.argv
+
+
+def timed(fn, n):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def mk(g, *shape, s=1.5):
+    return (torch.randn(*shape, device="cuda", generator=g) * s).bfloat16()
+
+
+def fwd_case(entry, G, H, N, d, check=True):
+    g = torch.Generator(device="cuda").manual_seed(N + d + G)
+    qs = [mk(g, H, N, d) for _ in range(G)]
+    k, v = mk(g, H, N, d), mk(g, H, N, d)
+    ks, vs = [k] * G, [v] * G
+    O = torch.empty(G, H, N, d, device="cuda", dtype=torch.float32)
+    L = torch.empty(G, H, N, device="cuda", dtype=torch.float32)
+    scale = d ** -0.5
+
+    def run():
+        call(entry, _lib.ptr_array(qs), _lib.ptr_array(ks), _lib.ptr_array(vs), _lib.ptr_array([O[i] for i in range(G)]),
+             _lib.ptr_array([L[i] for i in range(G)]), G, H, N, N, d, float(scale), stream())
+
+    ms = timed(run, iters)
+    fl = 4.0 * G * H * N * N * d
+    err = errl = float("nan")
+    if check:
+        s = torch.einsum("hnd,hkd->hnk", qs[G - 1].float(), k.float()) * scale
+        ref = torch.softmax(s, -1) @ v.float()
+        err, errl = rel(O[G - 1], ref), rel(L[G - 1], torch.logsumexp(s, -1))
+    print(f"{entry:22s} G={G} H={H} N={N:5d} d={d:3d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr O {err:.2e} LSE {errl:.2e}", flush=True)
+
+
+def bwd_case(H, N, d, M=0):
+    g = torch.Generator(device="cuda").manual_seed(N + d)
+    q, k, v = mk(g, H, N, d), mk(g, H, N, d), mk(g, H, N, d)
+    do = mk(g, H, N, d, s=1.0)
+    scale = d ** -0.5
+    O = torch.empty(1, H, N, d, device="cuda", dtype=torch.float32)
+    L = torch.empty(1, H, N, device="cuda", dtype=torch.float32)
+    entry = "gd_attn_fwd_sm100" if (N % 128 == 0 and d in (40, 80)) else "gd_attn_fwd_generic"
+    call(entry, _lib.ptr_array([q]), _lib.ptr_array([k]), _lib.ptr_array([v]), _lib.ptr_array([O[0]]), _lib.ptr_array([L[0]]), 1, H, N, N, d,
+         float(scale), stream())
+    delta = (do.float() * O[0]).sum(-1).contiguous()
+    dq = torch.empty(H, N, d, device="cuda", dtype=torch.float32)
+    ld = (N + 7) // 8 * 8
+    extra = rowmap = dl = None
+    if M:
+        rows = torch.randperm(N, device="cuda")[:M].sort().values.int()
+        rowmap = torch.full((N,), -1, device="cuda", dtype=torch.int32)
+        rowmap[rows.long()] = torch.arange(M, device="cuda", dtype=torch.int32)
+        extra = torch.randn(H, M, ld, device="cuda") * 0.01
+        dl = torch.ones(1, device="cuda")
+
+    def run():
+        call("gd_attn_bwd", 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N,
+             d, float(scale), stream())
+
+    ms = timed(run, iters)
+    fl = 6.0 * H * N * N * d
+    # fp32 reference
+    s = torch.einsum("hnd,hkd->hnk", q.float(), k.float()) * scale
+    p = torch.softmax(s, -1)
+    dp = torch.einsum("hnd,hkd->hnk", do.float(), v.float())
+    if M:
+        dp[:, rows.long(), :] += extra[:, :, :N]
+        # delta gets the extra term too in the real path; keep the same delta on both sides here
+    ds = p * (dp - delta[..., None])
+    ref = torch.einsum("hnk,hkd->hnd", ds, k.float()) * scale
+    print(f"gd_attn_bwd(dQ)        H={H} N={N:5d} d={d:3d} M={M:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr dQ {rel(dq, ref):.2e}",
+          flush=True)
+
+
+if only in (None, "fwd"):
+    fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
+    fwd_case("gd_attn_fwd_sm100", 5, 8, 4096, 40)
+    fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
+    fwd_case("gd_attn_fwd_sm100", 5, 8, 1024, 80)
+    if not quick:
+        fwd_case("gd_attn_fwd_sm100", 3, 8, 9216, 40, check=False)
+        fwd_case("gd_attn_fwd_generic", 3, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_generic", 3, 8, 256, 160)
+if only in (None, "bwd"):
+    bwd_case(8, 4096, 40)
+    bwd_case(8, 4096, 40, M=410)
+    bwd_case(8, 1024, 80)
+    if not quick:
+        bwd_case(8, 256, 160)
