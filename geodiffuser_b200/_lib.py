@@ -25,6 +25,7 @@ SIGNATURES = {
     "gd_morph": [P, I, I, I, I, I, P, P],
     "gd_attn_fwd_generic": [P, P, P, P, P, I, I, I, I, I, F, P],
     "gd_attn_fwd_sm100": [P, P, P, P, P, I, I, I, I, I, F, P],
+    "gd_attn_sm100_config": [I],
     "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, I, I, I, I, P, P, P],
     "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P],
     "gd_cast_f32_to_bf16": [P, P, L, P],
@@ -45,7 +46,7 @@ SIGNATURES = {
 _LIB = None
 HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
 LAUNCHES = 0  # CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
-KERNELS_PER_CALL = {"gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2}  # every other entry point launches one
+KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2}  # every other entry point launches one
 
 
 class GeoDiffuserB200Error(RuntimeError):

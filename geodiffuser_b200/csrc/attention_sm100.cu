@@ -59,6 +59,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+// same, for waits that are not latency critical (the TMA producer runs stages ahead): let the hardware park the thread for up to ~1 us per try
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity), "r"(1000u) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1) : "memory");
@@ -141,9 +151,26 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax polynomial for 2^f
+// (max relative error 7.5e-5, far below the 2^-9 of the bf16 P it feeds), exponent spliced in with one shift-add (LEA).
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = x + 12582912.0f;            // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+    const float f = x - (t - 12582912.0f);
+    float p = fmaf(f, 0.0551716648f, 0.2426111251f);
+    p = fmaf(p, f, 0.6932609677f);
+    p = fmaf(p, f, 0.9999280572f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));   // FMNMX3 on sm_100
+    return d;
+}
 
 // D = head_dim (40 or 80).  KB = number of 64-wide (128-byte) column blocks per operand row; KSTEPS = ceil(D/16); DV = O columns.
-template <int D>
+// POLY: 0 = every exponential on the MUFU; n > 0 = every n-th exponential is evaluated by ex2_poly on the FMA pipe instead.
+template <int D, int POLY>
 __global__ void __launch_bounds__(SM100_THREADS, (D <= 64) ? 2 : 1)
 attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params p) {
     constexpr int KB = (D + 63) / 64;
@@ -195,7 +222,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 4) {
-        // ================= TMA producer =================
+        // ================= TMA producer (runs up to two stages ahead: its waits are not latency critical) =================
         if (lane == 0) {
             mbar_expect_tx(q_full, OP_BYTES);
 #pragma unroll
@@ -203,11 +230,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
             for (int j = 0; j < nT; ++j) {
                 const int s = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(k_empty + s, ph ^ 1);
+                mbar_wait_relaxed(k_empty + s, ph ^ 1);
                 mbar_expect_tx(k_full + s, OP_BYTES);
 #pragma unroll
                 for (int b = 0; b < KB; ++b) tma_load_2d(sK + s * OP_BYTES + b * TILE_BYTES, &maps.k[g], k_full + s, b * 64, row_base + j * BN);
-                mbar_wait(v_empty + s, ph ^ 1);
+                mbar_wait_relaxed(v_empty + s, ph ^ 1);
                 mbar_expect_tx(v_full + s, OP_BYTES);
 #pragma unroll
                 for (int b = 0; b < KB; ++b) tma_load_2d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v[g], v_full + s, b * 64, row_base + j * BN);
@@ -252,55 +279,71 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
             }
         }
     } else {
-        // ================= softmax / correction / epilogue (warps 0-3) =================
+        // ================= softmax / correction / epilogue (warps 0-3): thread t owns query row t == TMEM lane t =================
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         const float scale2 = p.scale2;
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < nT; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            uint32_t sr[128];
+            uint32_t sr[BN];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(tmem + lane_off + COL_S + c * 32, sr + c * 32);
+            for (int c = 0; c < BN / 32; ++c) tmem_ld32(tmem + lane_off + COL_S + c * 32, sr + c * 32);
             tmem_wait_ld();
             tc_fence_before();
             if (lane == 0) mbar_arrive(s_free);      // S(j) is in registers: QK^T(j+1) may overwrite it
-            float mx = -INFINITY;
+            // row max: four independent FMNMX3 chains
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 128; ++c) mx = fmaxf(mx, __uint_as_float(sr[c]));
+            for (int c = 0; c < BN; c += 8) {
+                mx0 = max3(mx0, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
+                mx1 = max3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
+                mx2 = max3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
+                mx3 = max3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
+            }
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             const float m_cand = fmaxf(m_run, mx * scale2);
             const bool grow = (m_cand - m_run) > 8.0f;           // lazy rescale: tolerate up to 2^8 headroom
             const float m_new = grow ? m_cand : m_run;
             const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
             m_run = m_new;
-            float rs = 0.f;
-            uint32_t pk[64];
+            float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c) {
-                const float p0 = ex2(fmaf(__uint_as_float(sr[2 * c]), scale2, -m_new));
-                const float p1 = ex2(fmaf(__uint_as_float(sr[2 * c + 1]), scale2, -m_new));
-                rs += p0 + p1;
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-                pk[c] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            l_run = l_run * alpha + rs;
-            if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);                 // PV(j-1) has finished reading P and updating O
-                tc_fence_after();
-                if (__any_sync(0xffffffffu, grow)) {
+            for (int cc = 0; cc < BN / 32; ++cc) {
+                uint32_t pk[16];
 #pragma unroll
-                    for (int c = 0; c < DV / 16; ++c) {
-                        uint32_t orr[16];
-                        tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
-                        tmem_wait_ld();
+                for (int c = 0; c < 16; ++c) {
+                    const int e = cc * 32 + 2 * c;
+                    const float x0 = fmaf(__uint_as_float(sr[e]), scale2, -m_new);
+                    const float x1 = fmaf(__uint_as_float(sr[e + 1]), scale2, -m_new);
+                    const float p0 = (POLY > 0 && (e % POLY) == POLY - 1) ? ex2_poly(x0) : ex2(x0);
+                    const float p1 = (POLY > 0 && ((e + 1) % POLY) == POLY - 1) ? ex2_poly(x1) : ex2(x1);
+                    rs0 += p0;
+                    rs1 += p1;
+                    __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+                    pk[c] = *reinterpret_cast<uint32_t*>(&b2);
+                }
+                if (cc == 0 && j > 0) {
+                    // P(j) may overwrite P(j-1), and O may be corrected, only once PV(j-1) has completed.  Waiting here -- one chunk of
+                    // exponentials after the row max -- instead of in front of the exponentials keeps the MMA round trip
+                    // (p_full -> PV issue -> commit) off the softmax warps' critical path.
+                    mbar_wait(pv_done, (j - 1) & 1);
+                    tc_fence_after();
+                    if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
-                        for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
-                        tmem_st16(tmem + lane_off + COL_O + c * 16, orr);
+                        for (int c = 0; c < DV / 16; ++c) {
+                            uint32_t orr[16];
+                            tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
+                            tmem_st16(tmem + lane_off + COL_O + c * 16, orr);
+                        }
                     }
                 }
+                tmem_st16(tmem + lane_off + COL_P + cc * 16, pk);
             }
-            tmem_st32(tmem + lane_off + COL_P, pk);
-            tmem_st32(tmem + lane_off + COL_P + 32, pk + 32);
+            l_run = l_run * alpha + (rs0 + rs1);
             tmem_wait_st();
             tc_fence_before();
             if (lane == 0) mbar_arrive(p_full);
@@ -350,12 +393,12 @@ static EncodeTiledFn get_encode_fn() {
 }
 
 // (rows, d) bf16 row-major viewed as a 2-D tensor; box = 64 columns (128 B, zero-filled past d) x 128 rows, SWIZZLE_128B
-static int make_map(CUtensorMap* m, const void* base, long rows, int d) {
+static int make_map(CUtensorMap* m, const void* base, long rows, int d, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
     cuuint64_t gstr[1] = {(cuuint64_t)d * sizeof(bf16)};
-    cuuint32_t box[2] = {64, 128};
+    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -363,19 +406,33 @@ static int make_map(CUtensorMap* m, const void* base, long rows, int d) {
     return GD_OK;
 }
 
-template <int D> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
+static int g_poly = 4;   // tuning knob (gd_attn_sm100_config): every g_poly-th exponential goes to the FMA pipe
+
+template <int D, int POLY> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
     constexpr int KB = (D + 63) / 64;
     const size_t smem = (size_t)5 * KB * 128 * 128 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     dim3 grid(p.N / BM, p.H, G);
-    attn_fwd_sm100_kernel<D><<<grid, SM100_THREADS, smem, st>>>(maps, p);
+    attn_fwd_sm100_kernel<D, POLY><<<grid, SM100_THREADS, smem, st>>>(maps, p);
     GD_CHECK_LAUNCH();
     return GD_OK;
+}
+
+template <int D> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
+    switch (g_poly) {
+        case 0: return launch_sm100<D, 0>(maps, p, G, st);
+        case 2: return launch_sm100<D, 2>(maps, p, G, st);
+        case 3: return launch_sm100<D, 3>(maps, p, G, st);
+        case 4: return launch_sm100<D, 4>(maps, p, G, st);
+        case 6: return launch_sm100<D, 6>(maps, p, G, st);
+        case 8: return launch_sm100<D, 8>(maps, p, G, st);
+    }
+    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for poly=%d", g_poly);
 }
 
 }  // namespace gd
@@ -392,13 +449,22 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
     for (int g = 0; g < G; ++g) {
         GD_CHECK_ARG(q[g] && k[g] && v[g] && o[g] && lse[g]);
         int rc;
-        if ((rc = make_map(&maps.q[g], q[g], (long)H * N, d)) != GD_OK) return rc;
-        if ((rc = make_map(&maps.k[g], k[g], (long)H * N, d)) != GD_OK) return rc;
-        if ((rc = make_map(&maps.v[g], v[g], (long)H * N, d)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.q[g], q[g], (long)H * N, d, BM)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.k[g], k[g], (long)H * N, d, BN)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.v[g], v[g], (long)H * N, d, BN)) != GD_OK) return rc;
         p.o[g] = (float*)o[g];
         p.lse[g] = (float*)lse[g];
     }
     p.H = H; p.N = N; p.d = d; p.scale2 = scale * 1.4426950408889634f;
-    if (d == 40) return launch_sm100<40>(maps, p, G, (cudaStream_t)stream);
-    return launch_sm100<80>(maps, p, G, (cudaStream_t)stream);
+    if (d == 40) return dispatch_sm100<40>(maps, p, G, (cudaStream_t)stream);
+    return dispatch_sm100<80>(maps, p, G, (cudaStream_t)stream);
+}
+
+// Tuning knob of the tcgen05 forward (process-wide): poly in {0, 2, 3, 4, 6, 8} = every poly-th exponential of the online softmax is
+// evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (0: all MUFU).  Default 4.
+extern "C" int gd_attn_sm100_config(int poly) {
+    if (!(poly == 0 || poly == 2 || poly == 3 || poly == 4 || poly == 6 || poly == 8))
+        return set_error(GD_ERR_INVALID, "gd_attn_sm100_config(poly=%d): poly in {0,2,3,4,6,8}", poly);
+    g_poly = poly;
+    return GD_OK;
 }

@@ -68,6 +68,10 @@ int gd_attn_fwd_generic(const void* const* q_host, const void* const* k_host, co
 int gd_attn_fwd_sm100(const void* const* q_host, const void* const* k_host, const void* const* v_host, void* const* o_host,
                       void* const* lse_host, int G, int H, int N, int Nk, int d, float scale, void* stream);
 
+/* Tuning knob of gd_attn_fwd_sm100 (process-wide, not part of the reference surface): poly in {0,2,3,4,6,8} = every poly-th exponential
+ * of the online softmax is evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (0 = all MUFU; default 4). */
+int gd_attn_sm100_config(int poly);
+
 /* ---- (3) backward, fused with the attention-map losses --------------------------------------------------------------- */
 
 /* dO = g_out * coef[row] + g_loss * (*loss_scale) (bf16 out), delta[h,row] = sum_c dO*O (+ delta_extra[h, rowmap[row]] * *loss_scale).

@@ -100,6 +100,15 @@ def bwd_case(H, N, d, M=0):
           flush=True)
 
 
+if only == "sweep":
+    for poly in (0, 8, 6, 4, 3, 2):
+        if True:
+            call("gd_attn_sm100_config", poly)
+            print(f"--- poly={poly}", flush=True)
+            fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
+            fwd_case("gd_attn_fwd_sm100", 5, 8, 4096, 40)
+            fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
+            fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
 if only in (None, "fwd"):
     fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
     fwd_case("gd_attn_fwd_sm100", 5, 8, 4096, 40)
