@@ -94,7 +94,7 @@ def profile_end():
 def call(name, *args, tag=None):
     global LAUNCHES
     L_ = lib()
-    if PROFILE is not None and name in PROFILE["names"]:
+    if PROFILE is not None and name in PROFILE["names"] and not torch.cuda.is_current_stream_capturing():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(L_, name)(*args)

@@ -44,8 +44,7 @@ def register_attention_control_diffusers(model, controller, transform_coords=Non
 
 
 def set_attn_processor_for_edit(model, perform_edit=True, coords_base=(2, 3), coords_edit=(3, 4), use_cfg=True):
-    for name in model.unet.attn_processors.keys():
-        proc = model.unet.attn_processors[name]
+    for proc in model.unet.attn_processors.values():
         proc.perform_edit = perform_edit
         proc.controller.coords_base = coords_base
         proc.controller.coords_edit = coords_edit
@@ -152,6 +151,8 @@ class AttentionControl(abc.ABC):
             self.cur_att_layer = 0
             self.cur_step += 1
             self.between_steps()
+            if not (q.is_cuda and torch.cuda.is_current_stream_capturing()):
+                self.eager_passes = getattr(self, "eager_passes", 0) + 1   # graphs.py: caches are complete after one real evaluation
         return out
 
     def reset(self):
@@ -267,6 +268,7 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         self.store_attention_maps = False
         self.masks_cache_dict = {}
         self._res_cache = {}
+        self._arena = None          # editor.make_controller: per-model buffers that keep cache addresses stable across edits
         self._log_accum = None
         self.loss_log_dict = None
         self.loss_weight_dict = None
@@ -371,7 +373,7 @@ class AttentionGeometryEdit(_GeometryControllerBase):
             img_mask = self.image_mask.to(device=device, dtype=torch.float32)
             masks = geometry.build_masks(img_mask[-1].contiguous(), mnw[-1, 0].contiguous(), amodal.reshape(amodal.shape[-2:]).contiguous(), S)
             coords_S = geometry.reshape_transform_coords(self._coords512(transform_coords, device)[:1], in_mat_shape=(1, 1, S, S))[0]
-            c = Fn.ResolutionCache(S, masks, coords_S=coords_S, need_amodal=S * S > 32 ** 2)
+            c = Fn.ResolutionCache(S, masks, coords_S=coords_S, need_amodal=S * S > 32 ** 2, arena=self._arena)
             self._res_cache[S] = c
             self.masks_cache_dict[S] = dict(masks, t_coords_q=coords_S)
         return c
@@ -403,7 +405,7 @@ class AttentionGeometryRemover(_GeometryControllerBase):
                 self.image_mask = geometry.torch_dilate(self.image_mask.to(device=device, dtype=torch.float32)[:, None], 5)[:, 0]
                 self._dilated = True
             masks = geometry.build_masks(self.image_mask[-1].contiguous(), None, None, S)
-            c = Fn.ResolutionCache(S, masks, coords_S=None, need_amodal=False)
+            c = Fn.ResolutionCache(S, masks, coords_S=None, need_amodal=False, arena=self._arena)
             self._res_cache[S] = c
             self.masks_cache_dict[S] = dict(masks)
         return c

@@ -20,7 +20,11 @@ def set_body_dtype(dtype):
 
 
 def body_autocast():
-    return torch.autocast("cuda", dtype=torch.bfloat16, enabled=AUTOCAST_DTYPE == torch.bfloat16)
+    """kept for callers that wrap the UNet evaluation like the reference does (diffusion.py:39); the body now runs in the dtype of its
+    own weights (EditModel.unet), so this context never has to cast anything"""
+    import contextlib
+
+    return contextlib.nullcontext()
 
 
 class DDIMScheduler:
@@ -90,8 +94,10 @@ def diffusion_step(model, controller, latents, context, t, guidance_scale, low_r
     the graph; the latent step itself is never differentiated by the reference loop (only controller.loss is, editor.py:273)."""
     with body_autocast():
         if use_cfg:
+            from . import graphs
+
             latents_input = torch.cat([latents] * 2)
-            noise_pred = model.unet(latents_input, t, encoder_hidden_states=context)["sample"]
+            noise_pred = graphs.edit_pass(model, controller, latents_input, t, context)
             noise_pred_uncond, noise_prediction_text = noise_pred.chunk(2)
             latents_out = model.scheduler.step_cfg(noise_pred_uncond, noise_prediction_text, guidance_scale, t, latents)
             noise_pred_out = None

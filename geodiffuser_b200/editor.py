@@ -9,7 +9,7 @@ reference's; every tensor op on the path is a C-ABI CUDA launch (attention layer
 import numpy as np
 import torch
 
-from . import geometry, synth
+from . import geometry, graphs, synth
 from .attention_processors import (AttentionGeometryEdit, AttentionGeometryRemover, VanillaAttentionProcessor,
                                    register_attention_control_diffusers, set_attn_processor_for_edit)
 from .diffusion import body_autocast, diffusion_step
@@ -52,7 +52,7 @@ def ddim_inversion_loop(model, latent, context, guidance_scale=3.0, num_ddim_ste
     latents = latent.clone().detach().float()
     for t in reversed(sched.timesteps.tolist()):  # 0, 20, ..., 980 (DDIMInverseScheduler, leading spacing)
         with body_autocast():
-            noise_pred = model.unet(torch.cat([latents] * 2), t, encoder_hidden_states=context)["sample"]
+            noise_pred = graphs.inversion_pass(model, torch.cat([latents] * 2), t, context)
         eu, ec = noise_pred.chunk(2)
         latents = sched.next_step_cfg(eu, ec, guidance_scale, t, latents)
         all_latent.append(latents.detach())
@@ -205,6 +205,10 @@ def make_controller(model, staged, transform_in, edit_type, hp, num_ddim_steps=5
     cls = AttentionGeometryRemover if edit_type == "geometry_remover" else AttentionGeometryEdit
     controller = cls(["", ""], num_ddim_steps, cross_replace_steps=hp["cross_replace_steps"], self_replace_steps=hp["self_replace_steps"],
                      image_mask=None, empty_scale=0.0, use_all=False, obj_edit_step=hp["obj_edit_step"], device=device)
+    # cache buffers and captured graphs of the gradient-free passes live on the model, per controller kind, and are reused by the next edit
+    # (edits on one model are sequential: one live controller per model)
+    controller._arena = model.__dict__.setdefault("_arenas", {}).setdefault(cls.__name__, {})
+    controller._unet_graphs = model.__dict__.setdefault("_edit_graphs", {}).setdefault(cls.__name__, {})
     controller.image_mask = staged["obj_mask"][None].tile(2, 1, 1)
     controller.amodal_mask = geometry.torch_erode(mesh[None, None])  # editor.py:633
     if hp.get("loss_weights_dict") is not None:

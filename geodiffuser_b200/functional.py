@@ -40,15 +40,30 @@ class ResolutionCache:
     """Everything that depends only on (masks, correspondence field, S): built once per edit per attention resolution
     (the reference caches masks/coords per S, attention_processors.py:319-373, but re-rasterises the splat on every call)."""
 
-    def __init__(self, S, masks, coords_S=None, need_amodal=False):
+    def __init__(self, S, masks, coords_S=None, need_amodal=False, arena=None):
+        """`arena`: optional dict that outlives the edit (one per model and controller kind).  Everything a gradient-free pass reads from the
+        cache (masks, blend coefficients, splat index) is then kept at a fixed address and refreshed in place, so CUDA graphs captured for
+        one edit stay valid for the next (graphs.py)."""
+        def keep(name, t):
+            t = t.contiguous()
+            if arena is None:
+                return t
+            buf = arena.get((S, name))
+            if buf is None or buf.shape != t.shape or buf.dtype != t.dtype or buf.device != t.device:
+                arena[(S, name)] = buf = t.clone()
+                arena["generation"] = arena.get("generation", 0) + 1    # graphs that captured the old address are stale
+            else:
+                buf.copy_(t)
+            return buf
+
         self.S = S
         self.N = S * S
-        self.masks = {k: v.contiguous() for k, v in masks.items()}
+        self.masks = {k: keep(k, v) for k, v in masks.items()}
         dev = masks["mask_wo_edit"].device
         f = lambda n: self.masks[n].reshape(-1)
         self.m_edit, self.m_bg, self.m_inp, self.m_am = f("mask_new_warped"), f("mask_wo_edit"), f("mask_1_empty"), f("amodal_mask")
-        self.one_minus_m_edit = (1.0 - self.m_edit).contiguous()
-        self.m_inp_plus_bg = (self.m_inp + self.m_bg).contiguous()
+        self.one_minus_m_edit = keep("one_minus_m_edit", 1.0 - self.m_edit)
+        self.m_inp_plus_bg = keep("m_inp_plus_bg", self.m_inp + self.m_bg)
         rows = torch.nonzero(self.m_inp > 0.5).reshape(-1).to(torch.int32)
         self.rows = rows.contiguous()
         self.M = int(rows.numel())
@@ -59,7 +74,8 @@ class ResolutionCache:
         self.sum_bg, self.sum_edit, self.sum_inp = float(self.m_bg.sum()), float(self.m_edit.sum()), float(self.m_inp.sum())
         self.idx = self.dist2 = None
         if coords_S is not None:
-            self.idx, _, self.dist2 = geometry.splat_index(coords_S[None])
+            idx, _, dist2 = geometry.splat_index(coords_S[None])
+            self.idx, self.dist2 = keep("idx", idx), keep("dist2", dist2)
         self.knn_idx = self.knn_val = self.knn_w = None
         self.sum_w_am = 0.0
         if need_amodal:

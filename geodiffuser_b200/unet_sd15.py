@@ -243,9 +243,13 @@ class UNet2DConditionModel(nn.Module):
 
     # ---- the processor registry the reference's hook API drives (diffusers UNet2DConditionModel.attn_processors) ----
     def _attention_modules(self):
-        for name, m in self.named_modules():
-            if isinstance(m, Attention):
-                yield name, m
+        # the module tree is fixed after construction: walk it once (diffusers re-walks it on every access of `attn_processors`,
+        # which the reference's set_attn_processor_for_edit does 33 times per call and 67 times per edit)
+        mods = self.__dict__.get("_attn_mods")
+        if mods is None:
+            mods = [(name, m) for name, m in self.named_modules() if isinstance(m, Attention)]
+            self.__dict__["_attn_mods"] = mods
+        return mods
 
     @property
     def attn_processors(self):
@@ -264,6 +268,13 @@ class UNet2DConditionModel(nn.Module):
                 m.set_processor(processor)
 
     def forward(self, sample, timestep, encoder_hidden_states):
+        # the body runs in the dtype of its own weights (bf16 copy in channels_last = product setting, fp32 = parity setting); inputs are
+        # cast on entry (differentiable), so no autocast pass re-casts the weights on every evaluation
+        wdtype = self.conv_in.weight.dtype
+        sample = sample.to(wdtype)
+        if wdtype != torch.float32:
+            sample = sample.contiguous(memory_format=torch.channels_last)
+        encoder_hidden_states = encoder_hidden_states.to(wdtype)
         t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=sample.device)
         t = t.reshape(-1).to(sample.device).expand(sample.shape[0])
         temb = timestep_embedding(t, self.block_out[0]).to(sample.dtype)
@@ -285,7 +296,27 @@ class EditModel:
     Tokenizer / text encoder / VAE are out of scope (synthetic context embeddings and latents)."""
 
     def __init__(self, unet, scheduler, device):
-        self.unet, self.scheduler, self.device = unet, scheduler, device
+        self._unets = {torch.float32: unet}
+        self.scheduler, self.device = scheduler, device
+
+    @property
+    def unet(self):
+        """The UNet body in the caller precision selected by diffusion.set_body_dtype: the fp32 master (parity runs) or a bf16,
+        channels_last copy of it made on first use (the product / bench setting; same weight rounding autocast would apply per call)."""
+        from . import diffusion
+
+        dt = diffusion.AUTOCAST_DTYPE if self.device.type == "cuda" else torch.float32
+        if dt not in self._unets:
+            import copy
+
+            master = self._unets[torch.float32]
+            procs = master.attn_processors
+            master.set_attn_processor(None)          # processors (and the controller state behind them) are shared, not copied
+            u = copy.deepcopy(master).to(dt).to(memory_format=torch.channels_last)
+            master.set_attn_processor(procs)
+            u.set_attn_processor(procs)
+            self._unets[dt] = u
+        return self._unets[dt]
 
 
 def build_model(device="cuda", seed=1234, tiny=False):

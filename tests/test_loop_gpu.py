@@ -148,3 +148,20 @@ def test_edit_is_deterministic(tiny_model):
     a = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4)
     b = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4)
     assert torch.equal(a, b)
+
+
+def test_cuda_graph_replay_matches_eager(tiny_model):
+    """the gradient-free UNet passes replayed from CUDA graphs (graphs.py) give bit-identical latents to the eager loop"""
+    from geodiffuser_b200 import editor, graphs
+
+    try:
+        graphs.ENABLED = False
+        a = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=8)
+        graphs.ENABLED = True
+        tiny_model.__dict__.pop("_inversion_graphs", None)
+        b = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=8)
+        c = editor.perform_synthetic_edit(tiny_model, "remove", num_ddim_steps=8)   # a second edit reuses the inversion graph
+    finally:
+        graphs.ENABLED = True
+    assert torch.isfinite(c).all()
+    assert torch.equal(a, b)
