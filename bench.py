@@ -184,7 +184,7 @@ def run_ours(args):
     resident = lambda: editor.run_edit(model, staged, req["transform_in"], req["edit_type"])
     sampler = ClockSampler(local)
     sampler.start()
-    _lib.profile_begin(["gd_attn_fwd_sm100", "gd_attn_fwd_generic", "gd_attn_bwd", "gd_attn_probs", "gd_corr_max_partial"])
+    _lib.profile_begin(["gd_attn_fwd_sm100", "gd_attn_fwd_generic", "gd_attn_bwd", "gd_attn_bwd_sm100", "gd_attn_probs", "gd_corr_max_partial"])
     l0 = _lib.LAUNCHES
     ms_value = timed(resident, args.steps)
     launches = _lib.LAUNCHES - l0

@@ -28,6 +28,7 @@ SIGNATURES = {
     "gd_attn_sm100_config": [I],
     "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, I, I, I, I, P, P, P],
     "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P],
+    "gd_attn_bwd_sm100": [P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, F, P],
     "gd_cast_f32_to_bf16": [P, P, L, P],
     "gd_attn_probs": [P, P, P, P, I, I, I, I, I, F, P, I, P],
     "gd_corr_max_partial": [P, P, I, I, I, I, I, P, P, P, P],

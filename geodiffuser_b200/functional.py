@@ -273,8 +273,12 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
              ptr(s["g_loss"]) if has_loss else None, ptr(d_loss), ptr(s["o_e"]), ptr(s["delta_extra"]) if has_extra else None, rowmap, M,
              h, N, d, ptr(d_o), ptr(delta), stream())
         dq_e = torch.empty(h, N, d, device=dev, dtype=torch.float32)
-        call("gd_attn_bwd", 0, ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-             ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dq_e), h, N, Nk, d, float(spec.scale), stream())
+        if _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024 and s["ld"] % 4 == 0:
+            call("gd_attn_bwd_sm100", ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
+                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dq_e), h, N, d, float(spec.scale), stream(), tag=(h, N, d))
+        else:
+            call("gd_attn_bwd", 0, ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
+                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dq_e), h, N, Nk, d, float(spec.scale), stream())
         dq[ce0 * h:ce1 * h] = dq_e.to(q_dtype)
         dk = None
         if spec.is_cross and spec.kind == "edit":

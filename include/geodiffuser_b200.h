@@ -86,6 +86,12 @@ int gd_attn_bwd(int mode, const void* q, const void* k, const void* v, const voi
                 const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* out, int H, int N, int Nk,
                 int d, float scale, void* stream);
 
+/* Same operands and result as gd_attn_bwd mode 0 (dQ), tcgen05 / TMEM / TMA kernel for the self-attention levels:
+ * N == Nk, N % 128 == 0, d in {40, 80}; extra rows (if any) 16-byte aligned (ex_ld % 4 == 0). */
+int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
+                      const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* dq, int H, int N,
+                      int d, float scale, void* stream);
+
 int gd_cast_f32_to_bf16(const float* src, void* dst_bf16, long n, void* stream);
 
 /* P[h,m,:] = softmax row of q[h, rows[m] or m] against k[h] given lse (bf16 out, row stride ldp % 8 == 0, pad columns zero).

@@ -60,7 +60,7 @@ def fwd_case(entry, G, H, N, d, check=True):
     print(f"{entry:22s} G={G} H={H} N={N:5d} d={d:3d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr O {err:.2e} LSE {errl:.2e}", flush=True)
 
 
-def bwd_case(H, N, d, M=0):
+def bwd_case(H, N, d, M=0, sm100=False):
     g = torch.Generator(device="cuda").manual_seed(N + d)
     q, k, v = mk(g, H, N, d), mk(g, H, N, d), mk(g, H, N, d)
     do = mk(g, H, N, d, s=1.0)
@@ -82,8 +82,12 @@ def bwd_case(H, N, d, M=0):
         dl = torch.ones(1, device="cuda")
 
     def run():
-        call("gd_attn_bwd", 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N,
-             d, float(scale), stream())
+        if sm100:
+            call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N,
+                 d, float(scale), stream())
+        else:
+            call("gd_attn_bwd", 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N,
+                 d, float(scale), stream())
 
     ms = timed(run, iters)
     fl = 6.0 * H * N * N * d
@@ -96,7 +100,7 @@ def bwd_case(H, N, d, M=0):
         # delta gets the extra term too in the real path; keep the same delta on both sides here
     ds = p * (dp - delta[..., None])
     ref = torch.einsum("hnk,hkd->hnd", ds, k.float()) * scale
-    print(f"gd_attn_bwd(dQ)        H={H} N={N:5d} d={d:3d} M={M:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr dQ {rel(dq, ref):.2e}",
+    print(f"gd_attn_bwd{'_sm100' if sm100 else '      '}(dQ)  H={H} N={N:5d} d={d:3d} M={M:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr dQ {rel(dq, ref):.2e}",
           flush=True)
 
 
@@ -119,6 +123,14 @@ if only in (None, "fwd"):
         fwd_case("gd_attn_fwd_generic", 3, 8, 4096, 40)
         fwd_case("gd_attn_fwd_generic", 3, 8, 256, 160)
 if only in (None, "bwd"):
+    for poly in (0, 4):
+        call("gd_attn_sm100_config", poly)
+        print(f"--- poly={poly}")
+        bwd_case(8, 4096, 40, sm100=True)
+        bwd_case(8, 4096, 40, M=410, sm100=True)
+        bwd_case(8, 1024, 80, sm100=True)
+        bwd_case(8, 1024, 80, M=100, sm100=True)
+        bwd_case(2, 9216, 40, sm100=True)
     bwd_case(8, 4096, 40)
     bwd_case(8, 4096, 40, M=410)
     bwd_case(8, 1024, 80)

@@ -69,3 +69,46 @@ def test_sm100_rejects_unsupported_shapes():
     q = torch.zeros(1, 100, 40, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(_lib.GeoDiffuserB200Error):
         _run("gd_attn_fwd_sm100", [q], [q], [q], 1.0)
+
+
+@pytest.mark.parametrize("N,d,H,M", [(4096, 40, 8, 0), (4096, 40, 8, 410), (1024, 80, 8, 100), (128, 40, 1, 5), (256, 80, 2, 0), (2304, 40, 2, 64)])
+@pytest.mark.timeout(120)
+def test_sm100_backward_dq(N, d, H, M):
+    """tcgen05 dQ kernel vs the fp32 evaluation of dQ = scale * (P o (dO V^T + extra - delta)) K on the same bf16 inputs, and vs the mma.sync
+    kernel it replaces at these shapes; `extra` = dL/dP rows of the removal loss (random here), scaled by a device scalar."""
+    from geodiffuser_b200 import _lib
+    from geodiffuser_b200._lib import call, ptr, stream
+
+    g = torch.Generator(device="cuda").manual_seed(N + d + M)
+    mk = lambda s=1.5: (torch.randn(H, N, d, device="cuda", generator=g) * s).bfloat16()
+    q, k, v, do = mk(), mk(), mk(), mk(1.0)
+    scale = d ** -0.5
+    O, L = _run("gd_attn_fwd_sm100", [q], [k], [v], scale)
+    s = torch.einsum("hnd,hkd->hnk", q.float(), k.float()) * scale
+    p = torch.softmax(s, -1)
+    dp = torch.einsum("hnd,hkd->hnk", do.float(), v.float())
+    ld = (N + 7) // 8 * 8
+    extra = rowmap = dl = None
+    if M:
+        rows = torch.randperm(N, device="cuda", generator=g)[:M].sort().values.int()
+        rowmap = torch.full((N,), -1, device="cuda", dtype=torch.int32)
+        rowmap[rows.long()] = torch.arange(M, device="cuda", dtype=torch.int32)
+        extra = torch.randn(H, M, ld, device="cuda", generator=g) * 0.05
+        dl = torch.full((1,), 0.7, device="cuda")
+        dp[:, rows.long(), :] += 0.7 * extra[:, :, :N]
+    delta = (p * dp).sum(-1).contiguous()          # the row term of the softmax Jacobian (what gd_attn_bwd_prep produces on the path)
+    ref = torch.einsum("hnk,hkd->hnd", p * (dp - delta[..., None]), k.float()) * scale
+    out = []
+    for entry in ("gd_attn_bwd_sm100", "gd_attn_bwd"):
+        dq = torch.full((H, N, d), float("nan"), device="cuda", dtype=torch.float32)
+        if entry == "gd_attn_bwd":
+            call(entry, 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N, d,
+                 float(scale), stream())
+        else:
+            call(entry, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, d, float(scale),
+                 stream())
+        torch.cuda.synchronize()
+        out.append(dq)
+    assert torch.isfinite(out[0]).all()
+    assert relerr(out[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2       # bf16 operands / bf16 dS vs fp32 math (tolerance of the path: 2e-2)
+    assert relerr(out[0].cpu().numpy(), out[1].cpu().numpy()) <= 1e-2
