@@ -80,6 +80,15 @@ class ClockSampler:
         return out
 
 
+def kernel_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")) as f:
+            return json.load(f)["attn_fwd_sm100_kernel<40> G=3 H=8 N=4096"]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def attn_flops(tag):
     G, H, N, Nk, d = tag
     return 4.0 * G * H * N * Nk * d
@@ -207,9 +216,15 @@ def run_ours(args):
             ach = fl / (ms * 1e-3) / 1e12
             pk = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
             roof = {"kernel": "attn_fwd_sm100_kernel<40> (N=4096, d=40)", "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s",
-                    "frac": ach / pk, "traffic": None, "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+                    "frac": ach / pk, "traffic": kernel_traffic(), "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                     "launches": len(dom), "avg_launch_ms": ms / len(dom), "algorithmic_flops_per_launch": fl / len(dom),
                     "share_of_step_ms": {k: round(v / args.steps, 3) for k, v in by_kernel.items()}}
+            bw = [(ms, tag) for ms, tag in prof.get("gd_attn_bwd_sm100", []) if tag and tag[1] == 4096]
+            if bw:   # the matching backward (dQ) at the same level, same peak: 6*H*N^2*d algorithmic FLOP per launch
+                flb = sum(6.0 * t[0] * t[1] * t[1] * t[2] for _, t in bw)
+                msb = sum(m for m, _ in bw)
+                roof["backward"] = {"kernel": "attn_bwd_sm100_kernel<40> (N=4096, d=40)", "achieved": flb / (msb * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                    "frac": flb / (msb * 1e-3) / 1e12 / pk, "launches": len(bw), "avg_launch_ms": msb / len(bw)}
         line = {"metric": METRIC, "value": value, "unit": "edits/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",

@@ -411,7 +411,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
     constexpr int OP_BYTES = KB * TILE_BYTES;
     constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DS = 256, COL_DQ = 320;
     constexpr int TMEM_COLS = 512;
-    constexpr int NSTAGE = 2;
+    constexpr int NSTAGE = 2;                       // V ring (a V tile is free again once S/dP(j) are complete)
+    constexpr int KSTAGE = (D <= 64) ? 4 : 3;       // K ring: a K tile is needed at both ends of its step (scores, then dQ), so it is deeper
     constexpr int NEW = 8;                          // elementwise warps
     constexpr int NC = BN / 2;                      // key columns per elementwise thread
 
@@ -420,18 +421,18 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
     unsigned char* sQ = smem;
     unsigned char* sDO = sQ + OP_BYTES;
     unsigned char* sK = sDO + OP_BYTES;
-    unsigned char* sV = sK + NSTAGE * OP_BYTES;
+    unsigned char* sV = sK + KSTAGE * OP_BYTES;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTAGE * OP_BYTES);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;    // [2]
-    uint64_t* k_empty = bars + 3;   // [2]
-    uint64_t* v_full = bars + 5;    // [2]
-    uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;    // S(j) and dP(j) complete
-    uint64_t* s_free = bars + 10;   // both in registers (8 arrivals)
-    uint64_t* ds_full = bars + 11;  // dS(j) stored (8 arrivals)
-    uint64_t* dq_done = bars + 12;  // dQ += dS(j) K(j) complete
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* v_full = bars + 1;    // [2]
+    uint64_t* v_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;    // S(j) and dP(j) complete
+    uint64_t* s_free = bars + 6;    // both in registers (8 arrivals)
+    uint64_t* ds_full = bars + 7;   // dS(j) stored (8 arrivals)
+    uint64_t* dq_done = bars + 8;   // dQ += dS(j) K(j) complete
+    uint64_t* k_full = bars + 9;    // [KSTAGE]
+    uint64_t* k_empty = bars + 9 + KSTAGE;   // [KSTAGE]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * KSTAGE);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int h = blockIdx.y, q0 = blockIdx.x * BM;
@@ -441,7 +442,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+        for (int s = 0; s < KSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
         mbar_init(s_full, 1); mbar_init(s_free, NEW); mbar_init(ds_full, NEW); mbar_init(dq_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -467,10 +469,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
             for (int j = 0; j < nT; ++j) {
                 const int s = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
-                mbar_wait_relaxed(k_empty + s, ph ^ 1);
-                mbar_expect_tx(k_full + s, OP_BYTES);
+                const int ks = j % KSTAGE;
+                const uint32_t kph = (j / KSTAGE) & 1;
+                mbar_wait_relaxed(k_empty + ks, kph ^ 1);
+                mbar_expect_tx(k_full + ks, OP_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_2d(sK + s * OP_BYTES + b * TILE_BYTES, &maps.k, k_full + s, b * 64, row_base + j * BN);
+                for (int b = 0; b < KB; ++b) tma_load_2d(sK + ks * OP_BYTES + b * TILE_BYTES, &maps.k, k_full + ks, b * 64, row_base + j * BN);
                 mbar_wait_relaxed(v_empty + s, ph ^ 1);
                 mbar_expect_tx(v_full + s, OP_BYTES);
 #pragma unroll
@@ -486,11 +490,12 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
             auto issue_scores = [&](int j) {
                 const int s = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(k_full + s, ph);
+                const int kst = j % KSTAGE;
+                mbar_wait(k_full + kst, (j / KSTAGE) & 1);
                 mbar_wait(v_full + s, ph);
                 if (j > 0) mbar_wait(s_free, (j - 1) & 1);
                 tc_fence_after();
-                const uint32_t aK = smem_addr(sK + s * OP_BYTES), aV = smem_addr(sV + s * OP_BYTES);
+                const uint32_t aK = smem_addr(sK + kst * OP_BYTES), aV = smem_addr(sV + s * OP_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks) {
                     const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
@@ -508,7 +513,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
             issue_scores(0);
             for (int j = 0; j < nT; ++j) {
                 if (j + 1 < nT) issue_scores(j + 1);
-                const int s = j & 1;
+                const int s = j % KSTAGE;
                 mbar_wait(ds_full, j & 1);
                 tc_fence_after();
                 const uint32_t aK = smem_addr(sK + s * OP_BYTES);
@@ -667,7 +672,8 @@ template <int D> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Par
 
 template <int D, int POLY> static int launch_bwd_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
     constexpr int KB = (D + 63) / 64;
-    const size_t smem = (size_t)6 * KB * 128 * 128 + 256 + 1024;
+    constexpr int KSTAGE = (D <= 64) ? 4 : 3;
+    const size_t smem = (size_t)(4 + KSTAGE) * KB * 128 * 128 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_bwd_sm100_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

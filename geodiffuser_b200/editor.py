@@ -175,12 +175,12 @@ EXP_PARAMS = {
 }
 
 
-def synthetic_embeddings(seed=SEED, device="cuda"):
+def synthetic_embeddings(seed=SEED, device="cuda", image_size=IMAGE_SIZE):
     """context stand-ins: randn(2,77,768) text + randn uncond, CPU generator so every box sees the same values"""
     g = torch.Generator().manual_seed(seed + 1)
     text = torch.randn(1, 77, 768, generator=g).expand(2, 77, 768).contiguous()
     uncond = torch.randn(1, 77, 768, generator=g).expand(2, 77, 768).contiguous()
-    x0 = torch.randn(1, 4, IMAGE_SIZE // 8, IMAGE_SIZE // 8, generator=g)
+    x0 = torch.randn(1, 4, image_size // 8, image_size // 8, generator=g)
     return text.to(device), uncond.to(device), x0.to(device)
 
 
@@ -235,7 +235,7 @@ def run_edit(model, staged, transform_in, edit_type="geometry_editor", num_ddim_
         ddim_latents = ddim_inversion_loop(model, x0, torch.cat([uncond[:1], text[:1]]), hp["guidance_scale"], num_ddim_steps)
     else:
         gen = torch.Generator().manual_seed(seed + 2)
-        ddim_latents = [x0] + [torch.randn(1, 4, 64, 64, generator=gen).to(device) for _ in range(num_ddim_steps)]
+        ddim_latents = [x0] + [torch.randn(*x0.shape, generator=gen).to(device) for _ in range(num_ddim_steps)]
     x_t = ddim_latents[-1]
     latents, _, log = text2image_ldm_stable(
         model, ["", ""], controller, num_inference_steps=num_ddim_steps, guidance_scale=hp["guidance_scale"], latent=x_t,
@@ -259,18 +259,18 @@ def perform_geometric_edit(model, depth, image_mask, transform_in, text_embeddin
     return out, h2d, out.numel() * out.element_size()
 
 
-def synthetic_request(kind="rotate3d", seed=SEED, pin=True):
-    """host-side inputs of one synthetic edit request"""
-    image, depth, mask, T = synth.edit_inputs(kind)
-    text, uncond, x0 = synthetic_embeddings(seed, "cpu")
+def synthetic_request(kind="rotate3d", seed=SEED, pin=True, image_size=IMAGE_SIZE):
+    """host-side inputs of one synthetic edit request; image_size 768 = BASELINE.json configs[3] (96^2 latent)"""
+    image, depth, mask, T = synth.edit_inputs(kind, size=image_size)
+    text, uncond, x0 = synthetic_embeddings(seed, "cpu", image_size)
     if pin and torch.cuda.is_available():
         text, uncond, x0 = text.pin_memory(), uncond.pin_memory(), x0.pin_memory()
     edit_type = "geometry_remover" if kind == "remove" else "geometry_editor"
     return dict(depth=depth, image_mask=mask, transform_in=T, text_embeddings=text, uncond_embeddings=uncond, x0=x0, edit_type=edit_type)
 
 
-def perform_synthetic_edit(model, kind="rotate3d", num_ddim_steps=NUM_DDIM_STEPS, return_log=False, **kw):
+def perform_synthetic_edit(model, kind="rotate3d", num_ddim_steps=NUM_DDIM_STEPS, return_log=False, image_size=IMAGE_SIZE, **kw):
     """convenience wrapper used by the tests: device-side result of one synthetic edit"""
-    req = synthetic_request(kind, pin=False)
+    req = synthetic_request(kind, pin=False, image_size=image_size)
     staged, _ = stage_inputs(req["depth"], req["image_mask"], req["text_embeddings"], req["uncond_embeddings"], req["x0"], model.device)
     return run_edit(model, staged, req["transform_in"], req["edit_type"], num_ddim_steps=num_ddim_steps, return_log=return_log, **kw)

@@ -18,6 +18,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+import os
+
+BODY_CHANNELS_LAST = os.environ.get("GD_BODY_NCHW", "0") != "1"   # bf16 body layout: NHWC (cuDNN's native tensor-core layout) unless overridden
+
+
 class Attention(nn.Module):
     def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64):
         super().__init__()
@@ -272,7 +277,7 @@ class UNet2DConditionModel(nn.Module):
         # cast on entry (differentiable), so no autocast pass re-casts the weights on every evaluation
         wdtype = self.conv_in.weight.dtype
         sample = sample.to(wdtype)
-        if wdtype != torch.float32:
+        if wdtype != torch.float32 and BODY_CHANNELS_LAST:
             sample = sample.contiguous(memory_format=torch.channels_last)
         encoder_hidden_states = encoder_hidden_states.to(wdtype)
         t = timestep if torch.is_tensor(timestep) else torch.tensor([timestep], device=sample.device)
@@ -312,7 +317,9 @@ class EditModel:
             master = self._unets[torch.float32]
             procs = master.attn_processors
             master.set_attn_processor(None)          # processors (and the controller state behind them) are shared, not copied
-            u = copy.deepcopy(master).to(dt).to(memory_format=torch.channels_last)
+            u = copy.deepcopy(master).to(dt)
+            if BODY_CHANNELS_LAST:
+                u = u.to(memory_format=torch.channels_last)
             master.set_attn_processor(procs)
             u.set_attn_processor(procs)
             self._unets[dt] = u

@@ -165,3 +165,22 @@ def test_cuda_graph_replay_matches_eager(tiny_model):
         graphs.ENABLED = True
     assert torch.isfinite(c).all()
     assert torch.equal(a, b)
+
+
+@pytest.mark.timeout(300)
+def test_768_edit_runs_through_the_same_path(tiny_model):
+    """BASELINE.json configs[3]: 768x768 image -> 96^2 latent, attention levels 96/48/24/12 (N = 9216 and 2304 go through the tcgen05
+    kernels, 576 and 144 through the mma kernels).  The fp32 oracle cannot materialise (8, 9216, 9216) maps with autograd on this box, so
+    the gate here is structural: finite, deterministic, graph replay == eager, reference branch untouched by the edit."""
+    from geodiffuser_b200 import editor, graphs
+
+    try:
+        graphs.ENABLED = False
+        a = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4, image_size=768)
+        graphs.ENABLED = True
+        b = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4, image_size=768)
+    finally:
+        graphs.ENABLED = True
+    assert a.shape == (2, 4, 96, 96) and torch.isfinite(a).all()
+    assert torch.equal(a, b)
+    assert float((a[0] - a[1]).abs().max()) > 0      # the edit moved the edited sample, the reference sample is the inverted image
