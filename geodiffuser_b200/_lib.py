@@ -33,8 +33,8 @@ SIGNATURES = {
     "gd_attn_probs": [P, P, P, P, I, I, I, I, I, F, P, I, P],
     "gd_corr_max_partial": [P, P, I, I, I, I, I, P, P, P, P],
     "gd_attn_l1_losses": [P, P, P, P, P, P, P, F, F, F, F, F, I, I, I, P, P, I, P],
-    "gd_removal_finalize": [P, I, I, I, I, P, P, P, F, P, I, I, I, P, P, P, P, P, P],
-    "gd_loss_reduce": [P, I, P, I, P, P, F, P, P, P],
+    "gd_removal_finalize": [P, I, I, I, I, P, P, P, F, P, P, I, I, I, P, P, P, P, P, P],
+    "gd_loss_reduce": [P, I, P, I, P, P, P, F, P, P, P],
     "gd_amodal_knn": [P, I, P, P, P, P],
     "gd_amodal_target": [P, P, P, P, P, I, I, I, P, P, P],
     "gd_blend_rows": [P, P, P, P, I, I, I, P, I, P],

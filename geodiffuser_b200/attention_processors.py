@@ -268,10 +268,24 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         self.store_attention_maps = False
         self.masks_cache_dict = {}
         self._res_cache = {}
+        self._w_rem_dev = None      # device copy of loss_weight_dict[*]["removal"] (self, cross), see sync_device_weights
+        self._w_rem_host = None
         self._arena = None          # editor.make_controller: per-model buffers that keep cache addresses stable across edits
         self._log_accum = None
         self.loss_log_dict = None
         self.loss_weight_dict = None
+
+    def sync_device_weights(self, device):
+        """Mirrors the removal-loss weights (the only ones the adaptive schedule changes, optimization.py:7-105) into device memory, so that a
+        CUDA graph captured for one optimisation pass stays valid after the schedule has moved them.  Two 4-byte fills; no host sync."""
+        w = (float(self.loss_weight_dict["self"].get("removal", 0.0)), float(self.loss_weight_dict["cross"].get("removal", 0.0)))
+        if self._w_rem_dev is None or self._w_rem_dev.device != device:
+            self._w_rem_dev = torch.zeros(2, device=device, dtype=torch.float32)
+            self._w_rem_host = None
+        if self._w_rem_host != w:
+            self._w_rem_dev[0].fill_(w[0])
+            self._w_rem_dev[1].fill_(w[1])
+            self._w_rem_host = w
 
     # -- per-resolution cache -----------------------------------------------------------------------------------------
     def _coords512(self, transform_coords, device):
@@ -306,9 +320,14 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         cache = self._get_cache(S, transform_coords, q.device)
         with_loss = N >= 32 ** 2 and (not self.use_cfg)
         att = "cross" if is_cross else "self"
+        # the device copy of the removal weight is used only while it is known to be current (sync_device_weights); otherwise the host value
+        w_dev = None
+        if with_loss and self._w_rem_dev is not None and self._w_rem_dev.device == q.device and self._w_rem_host == (
+                float(self.loss_weight_dict["self"].get("removal", 0.0)), float(self.loss_weight_dict["cross"].get("removal", 0.0))):
+            w_dev = self._w_rem_dev[1:2] if is_cross else self._w_rem_dev[0:1]
         spec = Fn.LayerSpec(kind=self.KIND, is_cross=is_cross, heads=h, cb=tuple(self.coords_base), ce=tuple(self.coords_edit),
                             scale=float(scale), blend=self.cur_step < int(self.num_steps * self.obj_edit_step), with_loss=with_loss,
-                            weights=self.loss_weight_dict[att], cache=cache, log_accum=self._log_accum[1 if is_cross else 0])
+                            weights=self.loss_weight_dict[att], cache=cache, log_accum=self._log_accum[1 if is_cross else 0], w_rem_dev=w_dev)
         out, loss, _ = Fn.shared_attention_layer(q, k, v, spec)
         if N >= 32 ** 2:
             self.mask_wo_edit = cache.masks["mask_wo_edit"][None, None]

@@ -70,10 +70,11 @@ __global__ void __launch_bounds__(256) l1_losses_kernel(const L1Params p) {
 //   dex   = sum_k A_e * dL/dA_e = g_bg * p_bg + g_in * p_in       (the softmax-backward row correction)
 __global__ void removal_finalize_kernel(const float4* __restrict__ partial, int n_tiles, int H, int M, int S,
                                         const int* __restrict__ rows, const float* __restrict__ mask_in,
-                                        const float* __restrict__ mask_bg, float coef, float* __restrict__ term,
-                                        float2* __restrict__ g, int2* __restrict__ j, float* __restrict__ dex) {
+                                        const float* __restrict__ mask_bg, float coef, const float* __restrict__ w_dev,
+                                        float* __restrict__ term, float2* __restrict__ g, int2* __restrict__ j, float* __restrict__ dex) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= H * M) return;
+    if (w_dev) coef *= *w_dev;      // removal weight kept in device memory (adaptive schedule, CUDA-graph replay)
     const int h = i / M, m = i % M;
     float bi = -1.f, bb = -1.f; int ii = 0, ib = 0;
     for (int t = 0; t < n_tiles; ++t) {
@@ -115,6 +116,7 @@ struct LossReduceParams {
     const float* rem_terms; int n_rem;     // (H*M)
     float inv_sim, inv_mov, inv_amo, inv_smh, inv_smw, inv_rem;   // 1 / denominators
     float w_sim, w_mov, w_amo, w_sm, w_rem;
+    const float* w_rem_dev;                // if set, replaces w_rem
     float amodal_gate;                     // 0 when N <= 32^2 (attention_processors.py:596-597)
     float* terms; float* terms_accum;
 };
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const LossReduceParams
     if (threadIdx.x == 0) {
         const float sim = s[0] * p.inv_sim, mov = s[1] * p.inv_mov, amo = s[2] * p.inv_amo * p.amodal_gate;
         const float smo = s[3] * p.inv_smh + s[4] * p.inv_smw, rem = s[5] * p.inv_rem;
-        const float tot = p.w_sim * sim + p.w_mov * mov + p.w_rem * rem + p.w_sm * smo + p.w_amo * amo;
+        const float w_rem = p.w_rem_dev ? *p.w_rem_dev : p.w_rem;
+        const float tot = p.w_sim * sim + p.w_mov * mov + w_rem * rem + p.w_sm * smo + p.w_amo * amo;
         const float out[6] = {sim, mov, rem, smo, amo, tot};
         for (int k = 0; k < 6; ++k) { p.terms[k] = out[k]; if (p.terms_accum) p.terms_accum[k] += out[k]; }
     }
@@ -224,12 +227,12 @@ int gd_attn_l1_losses(const float* e, const float* r, const float* t, const floa
 }
 
 int gd_removal_finalize(const float* partial, int n_tiles, int H, int M, int S, const int* rows, const float* mask_in,
-                        const float* mask_bg, float coef, const void* a_b, int Nb, int Nk, int ld, float* term, float* g2, int* j2,
-                        float* delta_extra, float* extra, void* stream) {
+                        const float* mask_bg, float coef, const float* w_dev, const void* a_b, int Nb, int Nk, int ld, float* term, float* g2,
+                        int* j2, float* delta_extra, float* extra, void* stream) {
     GD_CHECK_ARG(partial && rows && mask_in && mask_bg && a_b && term && g2 && j2 && delta_extra && extra && H > 0 && M > 0 && n_tiles > 0);
     cudaStream_t st = (cudaStream_t)stream;
     removal_finalize_kernel<<<ceil_div((long)H * M, 128), 128, 0, st>>>((const float4*)partial, n_tiles, H, M, S, rows, mask_in, mask_bg,
-                                                                         coef, term, (float2*)g2, (int2*)j2, delta_extra);
+                                                                         coef, w_dev, term, (float2*)g2, (int2*)j2, delta_extra);
     GD_CHECK_LAUNCH();
     removal_extra_kernel<<<ceil_div((long)H * M * ld, 256), 256, 0, st>>>((const __nv_bfloat16*)a_b, (long)Nb * ld, ld, H, M, Nk,
                                                                            (const float2*)g2, (const int2*)j2, extra);
@@ -239,10 +242,10 @@ int gd_removal_finalize(const float* partial, int n_tiles, int H, int M, int S, 
 
 // inv[6] = 1/denominator of {sim, movement, amodal, smooth_h, smooth_w, removal}; w[5] = weights {sim, movement, amodal, smoothness, removal}
 int gd_loss_reduce(const float* partials, int n_part, const float* rem_terms, int n_rem, const float* inv6_host, const float* w5_host,
-                   float amodal_gate, float* terms6, float* terms_accum6, void* stream) {
+                   const float* w_rem_dev, float amodal_gate, float* terms6, float* terms_accum6, void* stream) {
     GD_CHECK_ARG(inv6_host && w5_host && terms6 && (partials || n_part == 0) && (rem_terms || n_rem == 0));
     LossReduceParams p = {partials, n_part, rem_terms, n_rem, inv6_host[0], inv6_host[1], inv6_host[2], inv6_host[3], inv6_host[4],
-                          inv6_host[5], w5_host[0], w5_host[1], w5_host[2], w5_host[3], w5_host[4], amodal_gate, terms6, terms_accum6};
+                          inv6_host[5], w5_host[0], w5_host[1], w5_host[2], w5_host[3], w5_host[4], w_rem_dev, amodal_gate, terms6, terms_accum6};
     loss_reduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(p);
     GD_CHECK_LAUNCH();
     return GD_OK;

@@ -13,8 +13,8 @@ from . import geometry, graphs, synth
 from .attention_processors import (AttentionGeometryEdit, AttentionGeometryRemover, VanillaAttentionProcessor,
                                    register_attention_control_diffusers, set_attn_processor_for_edit)
 from .diffusion import body_autocast, diffusion_step
-from .optimization import (_update_latent, adaptive_optimization_step_editing, adaptive_optimization_step_remover, norm_tensor,
-                           rescale_to_norm_)
+from .optimization import (_update_latent, adaptive_optimization_step_editing, adaptive_optimization_step_remover, apply_latent_update,
+                           norm_tensor, rescale_to_norm_)
 from ._lib import call, ptr, stream
 
 NUM_DDIM_STEPS = 50
@@ -106,12 +106,15 @@ def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, gui
             context_in = (context if context_save is None else context_save).detach().float().requires_grad_(True)
             for _ in range(num_optim_steps):
                 with torch.enable_grad():
-                    _, _ = diffusion_step(model, controller, latents_in, context_in[2:], t, guidance_scale, transform_coords=transform_coordinates,
-                                          use_cfg=False, return_noise=True)
+                    # forward with the loss-bearing layers + autograd.grad (diffusion_step(use_cfg=False) + optimization.py:201); replayed from
+                    # a CUDA graph after the first two passes of an edit (graphs.grad_pass)
+                    g_lat, g_ctx = graphs.grad_pass(model, controller, latents_in, context_in, t)
                     loss_val = controller.loss.detach().item()
                     if loss_val < best_loss:
                         best_latents, best_context, best_loss = latents_in, context_in, loss_val
-                    latents_in, context_new = _update_latent(latents_in, controller.loss, l_eff, controller.mask_new_warped[:1], context_in)
+                    latents_in, context_new = apply_latent_update(
+                        latents_in, g_lat if g_lat is not None else torch.zeros_like(latents_in), l_eff, controller.mask_new_warped[:1], context_in,
+                        g_ctx if g_ctx is not None else torch.zeros_like(context_in))
                     if num_optim_steps == 1:
                         best_latents, best_context = latents_in, context_new
                     context_in = context_new.detach().float().requires_grad_(True)

@@ -112,10 +112,13 @@ def warp_queries(q_base, cache):
 
 class LayerSpec:
     """Static description of one controller call."""
-    __slots__ = ("kind", "is_cross", "heads", "cb", "ce", "scale", "blend", "with_loss", "weights", "cache", "log_accum")
+    __slots__ = ("kind", "is_cross", "heads", "cb", "ce", "scale", "blend", "with_loss", "weights", "cache", "log_accum", "w_rem_dev")
+     # optional device scalar holding weights["removal"] (kept current by the controller; lets a captured pass follow the
+                         # adaptive schedule)
 
     def __init__(self, **kw):
-        for k, v in kw.items():
+        self.w_rem_dev = None   # optional device scalar holding weights["removal"], kept current by the controller: lets a captured pass
+        for k, v in kw.items():  # follow the adaptive schedule
             setattr(self, k, v)
 
 
@@ -218,13 +221,15 @@ def _forward_impl(q, k, v, spec):
         j2 = torch.empty(h * M, 2, device=dev, dtype=torch.int32)
         delta_extra = torch.empty(h, M, device=dev, dtype=torch.float32)
         extra = torch.empty(h, M, ld, device=dev, dtype=torch.float32)
-        call("gd_removal_finalize", ptr(partial), n_tiles, h, M, S, ptr(cache.rows), ptr(cache.m_inp), ptr(cache.m_bg), w_rem * inv_rem,
-             ptr(a_b), N, Nk, ld, ptr(rem_terms), ptr(g2), ptr(j2), ptr(delta_extra), ptr(extra), stream())
+        wdev = spec.w_rem_dev
+        call("gd_removal_finalize", ptr(partial), n_tiles, h, M, S, ptr(cache.rows), ptr(cache.m_inp), ptr(cache.m_bg),
+             inv_rem if wdev is not None else w_rem * inv_rem, ptr(wdev), ptr(a_b), N, Nk, ld, ptr(rem_terms), ptr(g2), ptr(j2), ptr(delta_extra),
+             ptr(extra), stream())
         del a_b, a_e, partial
     terms = torch.empty(6, device=dev, dtype=torch.float32)
     call("gd_loss_reduce", ptr(partials), n_part, ptr(rem_terms), h * M if M > 0 else 0,
          _lib.host_f32([inv_sim, inv_mov, inv_amo, inv_smh, inv_smh, inv_rem]), _lib.host_f32([w_sim, w_mov, w_amo, w_sm, w_rem]),
-         1.0 if use_amodal else 0.0, ptr(terms), ptr(spec.log_accum), stream())
+         ptr(spec.w_rem_dev), 1.0 if use_amodal else 0.0, ptr(terms), ptr(spec.log_accum), stream())
     saved.update(g_loss=g_loss, extra=extra, delta_extra=delta_extra, M=M)
     return out, terms, saved
 

@@ -10,18 +10,50 @@ those caches in per-model buffers that the next edit refreshes in place (functio
 serve every later edit of the same kind on that model.  A hand-made controller without an arena keeps its graphs to itself.
 The kernels of the path launch on torch's current stream (`_lib.stream()`), which is the capture stream inside `torch.cuda.graph`.
 """
+import contextlib
+import gc
+
 import torch
 
 from . import _lib
 
 ENABLED = True      # product default; tests compare against the eager path by switching it off
+GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as well
+
+
+@contextlib.contextmanager
+def _capture(graph, pool):
+    """torch.cuda.graph with the cyclic garbage collector paused: a collection in the middle of a capture may destroy an older CUDAGraph or
+    free its tensors, which invalidates the capture in progress"""
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, pool=pool):
+            yield
+    finally:
+        if was:
+            gc.enable()
+
+
+def _pool(model):
+    """one memory pool for every graph captured on a model: a dead graph's memory goes back to the pool instead of through cudaFree, so
+    re-capturing for the next edit does not pay for allocation"""
+    return model.__dict__.setdefault("_graph_pool", torch.cuda.graph_pool_handle())
+
+
+def _side_stream(model, dev):
+    """persistent warm-up stream (its cached allocations are reused by the next edit's warm-up pass)"""
+    st = model.__dict__.get("_graph_side_stream")
+    if st is None:
+        st = model.__dict__["_graph_side_stream"] = torch.cuda.Stream(device=dev)
+    return st
 
 
 class GraphedUNet:
     """unet(sample, t, context) -> eps for fixed shapes, replayed from a CUDA graph.  `warmup` eager evaluations first (they also build
     every lazily-created cache: resolution caches, tensor maps, cudaFuncSetAttribute), then one capture."""
 
-    def __init__(self, unet, sample, t, context, after_eval=None, warmup=1):
+    def __init__(self, unet, sample, t, context, after_eval=None, warmup=1, pool=None):
         dev = sample.device
         self.unet = unet
         self.sample = sample.detach().clone()
@@ -33,6 +65,7 @@ class GraphedUNet:
         self.path_launches = 0          # kernels of the C-ABI library inside the captured graph (re-counted on every replay)
         self.after_eval = after_eval
         self.warmup_left = warmup
+        self.pool = pool
 
     def _eval(self):
         out = self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
@@ -51,7 +84,7 @@ class GraphedUNet:
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             l0 = _lib.LAUNCHES
-            with torch.cuda.graph(g):
+            with _capture(g, self.pool):
                 self.out = self._eval()
             self.path_launches = _lib.LAUNCHES - l0
             _lib.LAUNCHES = l0          # capturing launches nothing
@@ -80,7 +113,7 @@ def edit_pass(model, controller, latents_input, t, context):
     key = (controller_key(controller), tuple(latents_input.shape), id(model.unet), arena.get("generation", 0) if arena is not None else -1)
     g = store.get(key)
     if g is None:
-        g = store[key] = GraphedUNet(model.unet, latents_input, t, context)
+        g = store[key] = GraphedUNet(model.unet, latents_input, t, context, pool=_pool(model))
     step, layer = controller.cur_step, controller.cur_att_layer
     out = g(latents_input, t, context)
     # eager evaluation and capture both walk the 32 layers through AttentionControl.__call__, a replay does not: leave the counters where one
@@ -98,5 +131,85 @@ def inversion_pass(model, latents_input, t, context):
     key = (tuple(latents_input.shape), tuple(context.shape), id(model.unet))
     g = store.get(key)
     if g is None:
-        g = store[key] = GraphedUNet(model.unet, latents_input, t, context)
+        g = store[key] = GraphedUNet(model.unet, latents_input, t, context, pool=_pool(model))
     return g(latents_input, t, context)
+
+
+class GraphedGradPass:
+    """One optimisation pass -- UNet forward under autograd with the loss-bearing attention layers, then d loss / d (latents, context)
+    (editor.py:239-253 + optimization.py:201 in the reference) -- captured as ONE graph: forward, the fused layers' backward kernels and
+    torch's backward of the body.  Static inputs: latents, context, timestep; static outputs: loss, the two gradients; the controller's
+    log accumulator is a static buffer already.  Everything that changes between passes lives in device memory (the removal weight:
+    controller.sync_device_weights) or in the key (all other weights, the controller flags)."""
+
+    def __init__(self, model, latents, context, t):
+        self.model = model          # (no reference to the controller: the graph is stored on it and must die with it, by refcount)
+        self.latents = latents.detach().clone().requires_grad_(True)
+        self.context = context.detach().clone().requires_grad_(True)
+        self.t = torch.zeros(1, device=latents.device, dtype=torch.int64)
+        self.graph = None
+        self.loss = self.g_lat = self.g_ctx = None
+        self.num_layers = 0
+        self.path_launches = 0
+
+    def _run(self, c):
+        with torch.enable_grad():
+            self.model.unet(self.latents, self.t, encoder_hidden_states=self.context[self.context.shape[0] // 2:])
+            g = torch.autograd.grad(c.loss, [self.latents, self.context], allow_unused=True)
+        return c.loss.detach(), g[0], g[1]
+
+    def __call__(self, c, latents, context, t):
+        self.latents.data.copy_(latents.detach())
+        self.context.data.copy_(context.detach())
+        self.t.fill_(int(t))
+        if self.graph is None:
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            step, layers = c.cur_step, c.loss_log_dict["num_layers"]
+            l0 = _lib.LAUNCHES
+            with _capture(g, _pool(self.model)):
+                self.loss, self.g_lat, self.g_ctx = self._run(c)
+            self.path_launches, _lib.LAUNCHES = _lib.LAUNCHES - l0, l0
+            self.num_layers = c.loss_log_dict["num_layers"] - layers
+            c.cur_step, c.loss_log_dict["num_layers"] = step, layers
+            self.graph = g
+        self.graph.replay()
+        _lib.LAUNCHES += self.path_launches
+        c.loss = self.loss
+        c.cur_step += 1
+        c.loss_log_dict["num_layers"] += self.num_layers
+        return self.g_lat, self.g_ctx
+
+
+def grad_pass(model, controller, latents, context, t):
+    """-> (d loss / d latents, d loss / d context) of one optimisation pass; controller.loss and controller.loss_log_dict hold the loss and its
+    logged terms afterwards, as after the reference's diffusion_step(use_cfg=False).  `context` is the full [uncond, text] stack (the UNet sees
+    its text half, editor.py:250).  First occurrence of a controller state: eager, on a side stream (which doubles as the warm-up a backward
+    capture needs); second: capture; then replay."""
+    dev = latents.device
+
+    def eager():
+        with torch.enable_grad():
+            model.unet(latents, t, encoder_hidden_states=context[context.shape[0] // 2:])
+            g = torch.autograd.grad(controller.loss, [latents, context], allow_unused=True)
+        return g
+
+    if not (ENABLED and GRAD_ENABLED) or not latents.is_cuda:
+        return eager()
+    controller.sync_device_weights(dev)
+    store = controller.__dict__.setdefault("_grad_graphs", {})
+    lw = controller.loss_weight_dict
+    weights = tuple(sorted((a, k, float(v)) for a in ("self", "cross") for k, v in lw[a].items() if k != "removal"))
+    key = (controller_key(controller), weights, tuple(latents.shape), tuple(context.shape), id(model.unet))
+    g = store.get(key)
+    if g is None:
+        store[key] = "warm"
+        side = _side_stream(model, dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            out = eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        return out
+    if g == "warm":
+        g = store[key] = GraphedGradPass(model, latents, context, t)
+    return g(controller, latents, context, t)

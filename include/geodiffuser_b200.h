@@ -111,15 +111,17 @@ int gd_attn_l1_losses(const float* e, const float* r, const float* t, const floa
                       float* grad, float* partials, int n_partials, void* stream);
 
 /* attention_processors.py:259-266: distance weight, log terms, and the two non-zero gradient entries per row; extra (H,M,ld) and
- * delta_extra (H,M) feed gd_attn_bwd_prep / gd_attn_bwd.  coef = removal weight / (sum(mask_inpaint) * H + 1e-8). */
+ * delta_extra (H,M) feed gd_attn_bwd_prep / gd_attn_bwd.  coef = removal weight / (sum(mask_inpaint) * H + 1e-8); if w_dev (device scalar) is given, coef is
+ * multiplied by *w_dev on the device: the adaptive schedule (optimization.py:7-105) changes that weight between passes of a captured graph. */
 int gd_removal_finalize(const float* partial, int n_tiles, int H, int M, int S, const int* rows, const float* mask_in,
-                        const float* mask_bg, float coef, const void* a_b_bf16, int Nb, int Nk, int ld, float* term, float* g2, int* j2,
-                        float* delta_extra, float* extra, void* stream);
+                        const float* mask_bg, float coef, const float* w_dev, const void* a_b_bf16, int Nb, int Nk, int ld, float* term,
+                        float* g2, int* j2, float* delta_extra, float* extra, void* stream);
 
 /* terms6 = {sim, movement, removal, smoothness, amodal, weighted total}; terms_accum6 (or NULL) += terms6.
- * inv6_host = 1/denominators {sim, movement, amodal, smooth_h, smooth_w, removal}; w5_host = weights {sim, movement, amodal, smoothness, removal} */
+ * inv6_host = 1/denominators {sim, movement, amodal, smooth_h, smooth_w, removal}; w5_host = weights {sim, movement, amodal, smoothness, removal};
+ * w_rem_dev (device scalar or NULL) overrides the removal weight */
 int gd_loss_reduce(const float* partials, int n_part, const float* rem_terms, int n_rem, const float* inv6_host, const float* w5_host,
-                   float amodal_gate, float* terms6, float* terms_accum6, void* stream);
+                   const float* w_rem_dev, float amodal_gate, float* terms6, float* terms_accum6, void* stream);
 
 /* attention_sharing.py:68-105 interpolate_from_mask: nearest-4 foreground pixels + weights (mask/grid only: once per resolution). */
 int gd_amodal_knn(const float* m_edit, int S, int* idx4, float* val4, float* w, void* stream);

@@ -20,13 +20,8 @@ def timed(name, fn):
 
 graphs.inversion_pass = timed("inversion_pass", graphs.inversion_pass)
 graphs.edit_pass = timed("cfg_pass(unet)", graphs.edit_pass)
-_ds = diffusion.diffusion_step
-def ds(model, controller, latents, context, t, g, *a, **k):
-    if k.get("use_cfg", True) is False:
-        return timed("opt_pass fwd", _ds)(model, controller, latents, context, t, g, *a, **k)
-    return _ds(model, controller, latents, context, t, g, *a, **k)
-editor.diffusion_step = ds
-editor._update_latent = timed("opt_pass bwd+update", optimization._update_latent)
+graphs.grad_pass = timed("opt_pass fwd+bwd", graphs.grad_pass)
+editor.apply_latent_update = timed("opt_pass update", optimization.apply_latent_update)
 editor.make_controller = timed("make_controller (geometry)", editor.make_controller)
 editor.ddim_inversion_loop = timed("[ddim_inversion_loop whole]", editor.ddim_inversion_loop)
 editor.text2image_ldm_stable = timed("[text2image whole]", editor.text2image_ldm_stable)

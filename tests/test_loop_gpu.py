@@ -151,10 +151,12 @@ def test_edit_is_deterministic(tiny_model):
 
 
 def test_cuda_graph_replay_matches_eager(tiny_model):
-    """the gradient-free UNet passes replayed from CUDA graphs (graphs.py) give bit-identical latents to the eager loop"""
+    """the gradient-free UNet passes replayed from CUDA graphs (graphs.py) give bit-identical latents to the eager loop (the optimisation
+    pass is kept eager here: under capture cuBLAS / cuDNN may pick other algorithms for the body's backward, see the next test)"""
     from geodiffuser_b200 import editor, graphs
 
     try:
+        graphs.GRAD_ENABLED = False
         graphs.ENABLED = False
         a = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=8)
         graphs.ENABLED = True
@@ -162,7 +164,7 @@ def test_cuda_graph_replay_matches_eager(tiny_model):
         b = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=8)
         c = editor.perform_synthetic_edit(tiny_model, "remove", num_ddim_steps=8)   # a second edit reuses the inversion graph
     finally:
-        graphs.ENABLED = True
+        graphs.ENABLED = graphs.GRAD_ENABLED = True
     assert torch.isfinite(c).all()
     assert torch.equal(a, b)
 
@@ -175,12 +177,69 @@ def test_768_edit_runs_through_the_same_path(tiny_model):
     from geodiffuser_b200 import editor, graphs
 
     try:
+        graphs.GRAD_ENABLED = False
         graphs.ENABLED = False
         a = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4, image_size=768)
         graphs.ENABLED = True
         b = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4, image_size=768)
     finally:
-        graphs.ENABLED = True
+        graphs.ENABLED = graphs.GRAD_ENABLED = True
     assert a.shape == (2, 4, 96, 96) and torch.isfinite(a).all()
     assert torch.equal(a, b)
     assert float((a[0] - a[1]).abs().max()) > 0      # the edit moved the edited sample, the reference sample is the inverted image
+
+
+@pytest.mark.parametrize("kind", ["rotate3d", "remove"])
+def test_graphed_gradient_pass_matches_eager(tiny_model, kind):
+    """One optimisation pass (loss, logged terms, d loss / d latent, d loss / d context) replayed from the captured forward + backward graph
+    against the eager pass on the same inputs, before and after the adaptive schedule has moved the removal weight (which the graph reads from
+    device memory).  Not bit-exact: inside a capture the body's cuBLAS / cuDNN calls may select other algorithms; 1e-2 covers that."""
+    from geodiffuser_b200 import editor, graphs
+    from geodiffuser_b200.attention_processors import register_attention_control_diffusers, set_attn_processor_for_edit
+    from geodiffuser_b200.editor import EXP_PARAMS
+
+    rel = lambda a, b: float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+    model = tiny_model
+    edit_type = "geometry_remover" if kind == "remove" else "geometry_editor"
+    hp = dict(EXP_PARAMS[edit_type])
+    req = editor.synthetic_request(kind, pin=False)
+    staged, _ = editor.stage_inputs(req["depth"], req["image_mask"], req["text_embeddings"], req["uncond_embeddings"], req["x0"], model.device)
+    c, tc = editor.make_controller(model, staged, req["transform_in"], edit_type, hp, 10)
+    register_attention_control_diffusers(model, c, tc)
+    c._ensure_mask_new_warped(tc, model.device)
+    model.scheduler.set_timesteps(10)
+    set_attn_processor_for_edit(model, coords_base=(0, 1), coords_edit=(1, 2), use_cfg=False)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x0 = staged["x0"]
+    lat = torch.cat([x0, x0 + 0.3 * torch.randn(x0.shape, device="cuda", generator=g)]).float()
+    ctx = torch.cat([staged["uncond"], staged["text"][:1], staged["text"][:1] + 0.3 * torch.randn(1, 77, 768, device="cuda", generator=g)]).float()
+
+    def one_pass(graphed):
+        graphs.GRAD_ENABLED = graphed
+        editor.clear_controller_loss(c)
+        c.cur_step = 2
+        li, ci = lat.clone().requires_grad_(True), ctx.clone().requires_grad_(True)
+        with torch.enable_grad():
+            gl, gc = graphs.grad_pass(model, c, li, ci, 801)
+        log = editor.convert_loss_log_to_numpy(c.loss_log_dict)
+        return float(c.loss), log, gl.clone(), None if gc is None else gc.clone()
+
+    try:
+        for w_scale in (1.0, 1.3):          # second round: after an adaptive-schedule move of the removal weight
+            c.loss_weight_dict["self"]["removal"] *= w_scale
+            ref = one_pass(False)
+            one_pass(True)                  # first graphed occurrence: eager on the side stream
+            got = one_pass(True)            # capture (first round) / replay
+            got2 = one_pass(True)           # replay
+            for r in (got, got2):
+                assert abs(r[0] - ref[0]) <= 1e-2 * abs(ref[0])
+                for att in ("self", "cross"):
+                    for k, v in ref[1][att].items():
+                        assert abs(r[1][att][k] - v) <= 1e-2 * max(abs(v), 0.05), (att, k)
+                assert r[1]["num_layers"] == ref[1]["num_layers"]
+                assert rel(r[2][-1], ref[2][-1]) <= 1e-2
+                assert float(r[2][0].abs().max()) == 0.0
+                if ref[3] is not None and float(ref[3].abs().max()) > 0:
+                    assert rel(r[3][-1], ref[3][-1]) <= 1e-2
+    finally:
+        graphs.GRAD_ENABLED = True
