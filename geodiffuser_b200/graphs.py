@@ -22,15 +22,25 @@ GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as 
 
 
 @contextlib.contextmanager
-def _capture(graph, pool):
-    """torch.cuda.graph with the cyclic garbage collector paused: a collection in the middle of a capture may destroy an older CUDAGraph or
-    free its tensors, which invalidates the capture in progress"""
+def _capture(graph, pool, stream):
+    """Stream capture into `graph` on `stream`.  torch.cuda.graph() would also run gc.collect() and torch.cuda.empty_cache() first; an edit
+    captures one graph per request, and an emptied allocator cache makes every eager allocation after it pay for cudaMalloc again, so the capture
+    is driven by hand.  The cyclic garbage collector is paused: a collection in the middle of a capture may destroy an older CUDAGraph or free
+    its tensors, which invalidates the capture in progress."""
     was = gc.isenabled()
     gc.disable()
+    cur = torch.cuda.current_stream(stream.device)
+    torch.cuda.synchronize(stream.device)
+    stream.wait_stream(cur)
     try:
-        with torch.cuda.graph(graph, pool=pool):
-            yield
+        with torch.cuda.stream(stream):
+            graph.capture_begin(pool=pool)
+            try:
+                yield
+            finally:
+                graph.capture_end()
     finally:
+        cur.wait_stream(stream)
         if was:
             gc.enable()
 
@@ -53,7 +63,7 @@ class GraphedUNet:
     """unet(sample, t, context) -> eps for fixed shapes, replayed from a CUDA graph.  `warmup` eager evaluations first (they also build
     every lazily-created cache: resolution caches, tensor maps, cudaFuncSetAttribute), then one capture."""
 
-    def __init__(self, unet, sample, t, context, after_eval=None, warmup=1, pool=None):
+    def __init__(self, unet, sample, t, context, after_eval=None, warmup=1, pool=None, stream=None):
         dev = sample.device
         self.unet = unet
         self.sample = sample.detach().clone()
@@ -66,6 +76,7 @@ class GraphedUNet:
         self.after_eval = after_eval
         self.warmup_left = warmup
         self.pool = pool
+        self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
 
     def _eval(self):
         out = self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
@@ -82,9 +93,8 @@ class GraphedUNet:
                 self.warmup_left -= 1
                 return self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
             g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
             l0 = _lib.LAUNCHES
-            with _capture(g, self.pool):
+            with _capture(g, self.pool, self.stream):
                 self.out = self._eval()
             self.path_launches = _lib.LAUNCHES - l0
             _lib.LAUNCHES = l0          # capturing launches nothing
@@ -113,7 +123,7 @@ def edit_pass(model, controller, latents_input, t, context):
     key = (controller_key(controller), tuple(latents_input.shape), id(model.unet), arena.get("generation", 0) if arena is not None else -1)
     g = store.get(key)
     if g is None:
-        g = store[key] = GraphedUNet(model.unet, latents_input, t, context, pool=_pool(model))
+        g = store[key] = GraphedUNet(model.unet, latents_input, t, context, pool=_pool(model), stream=_side_stream(model, latents_input.device))
     step, layer = controller.cur_step, controller.cur_att_layer
     out = g(latents_input, t, context)
     # eager evaluation and capture both walk the 32 layers through AttentionControl.__call__, a replay does not: leave the counters where one
@@ -131,7 +141,7 @@ def inversion_pass(model, latents_input, t, context):
     key = (tuple(latents_input.shape), tuple(context.shape), id(model.unet))
     g = store.get(key)
     if g is None:
-        g = store[key] = GraphedUNet(model.unet, latents_input, t, context, pool=_pool(model))
+        g = store[key] = GraphedUNet(model.unet, latents_input, t, context, pool=_pool(model), stream=_side_stream(model, latents_input.device))
     return g(latents_input, t, context)
 
 
@@ -164,10 +174,9 @@ class GraphedGradPass:
         self.t.fill_(int(t))
         if self.graph is None:
             g = torch.cuda.CUDAGraph()
-            torch.cuda.synchronize()
             step, layers = c.cur_step, c.loss_log_dict["num_layers"]
             l0 = _lib.LAUNCHES
-            with _capture(g, _pool(self.model)):
+            with _capture(g, _pool(self.model), _side_stream(self.model, latents.device)):
                 self.loss, self.g_lat, self.g_ctx = self._run(c)
             self.path_launches, _lib.LAUNCHES = _lib.LAUNCHES - l0, l0
             self.num_layers = c.loss_log_dict["num_layers"] - layers
