@@ -312,6 +312,9 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
             h = q.shape[0] // (2 * self.batch_size)
         else:
             h = q.shape[0] // self.batch_size
+        n_entries = int(self.coords_edit[1])          # the edit sample is the last batch entry (attention_processors.py:56-67)
+        if q.shape[0] % n_entries == 0 and q.shape[0] // n_entries != h:
+            h = q.shape[0] // n_entries               # batch without the dead unconditional reference sample (diffusion.diffusion_step)
         if not (is_cross or (self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1])):
             return Fn.plain_attention(q, k, v, scale, h)
         self._ensure_device_state(q.device)

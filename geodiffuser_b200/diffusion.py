@@ -89,11 +89,25 @@ class DDIMScheduler:
 
 
 def diffusion_step(model, controller, latents, context, t, guidance_scale, low_resource=False, transform_coords=None, use_cfg=True,
-                   return_noise=False):
+                   return_noise=False, skip_uncond_reference=False):
     """diffusion.py:40-59.  With use_cfg=False the UNet runs under autograd (the caller enables grad) and the returned noise carries
-    the graph; the latent step itself is never differentiated by the reference loop (only controller.loss is, editor.py:273)."""
+    the graph; the latent step itself is never differentiated by the reference loop (only controller.loss is, editor.py:273).
+
+    skip_uncond_reference: the reference loop evaluates the batch [uncond ref, uncond edit, cond ref, cond edit] and then REPLACES the reference
+    latent by the stored inversion latent (editor.py:375-377), so the reference sample's noise prediction is never used and its unconditional
+    evaluation feeds nothing (nobody attends to it).  With this flag that dead quarter of the batch is not evaluated: the UNet sees
+    [uncond edit, cond ref, cond edit] (controller coords (1,2) / (2,3)) and latents_out[0] is returned unchanged for the caller to overwrite.
+    The edited sample's result is identical."""
     with body_autocast():
-        if use_cfg:
+        if use_cfg and skip_uncond_reference:
+            from . import graphs
+
+            assert latents.shape[0] == 2 and context.shape[0] == 4 and not return_noise
+            noise_pred = graphs.edit_pass(model, controller, torch.cat([latents[1:], latents]), t, context[1:])
+            latents_out = latents.detach().float().clone()
+            latents_out[1:] = model.scheduler.step_cfg(noise_pred[0:1], noise_pred[2:3], guidance_scale, t, latents[1:])
+            noise_pred_out = None
+        elif use_cfg:
             from . import graphs
 
             latents_input = torch.cat([latents] * 2)

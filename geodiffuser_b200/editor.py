@@ -20,6 +20,7 @@ from ._lib import call, ptr, stream
 NUM_DDIM_STEPS = 50
 IMAGE_SIZE = 512
 SEED = 1234  # editor.py:47
+SKIP_DEAD_UNCOND_REFERENCE = True   # diffusion.diffusion_step(skip_uncond_reference=...): result-preserving, 1/4 of every CFG pass
 
 
 def clear_controller_loss(controller):
@@ -137,8 +138,14 @@ def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, gui
             continue
         elif context_save is not None:
             context = context_save
-        set_attn_processor_for_edit(model, coords_base=(2, 3), coords_edit=(3, 4), use_cfg=True)
-        latents = diffusion_step(model, controller, latents, context, t, guidance_scale, transform_coords=transform_coordinates)
+        # the reference latent is overwritten below whenever the inversion trajectory is given, which makes its unconditional evaluation dead work
+        skip = SKIP_DEAD_UNCOND_REFERENCE and ddim_latents is not None
+        if skip:
+            set_attn_processor_for_edit(model, coords_base=(1, 2), coords_edit=(2, 3), use_cfg=True)
+        else:
+            set_attn_processor_for_edit(model, coords_base=(2, 3), coords_edit=(3, 4), use_cfg=True)
+        latents = diffusion_step(model, controller, latents, context, t, guidance_scale, transform_coords=transform_coordinates,
+                                 skip_uncond_reference=skip)
         if ddim_latents is not None:
             i_n = len(ddim_latents) - 2 - i
             latents = torch.cat([ddim_latents[i_n].to(latents), latents[-1:].detach()], 0)  # editor.py:375-377

@@ -243,3 +243,23 @@ def test_graphed_gradient_pass_matches_eager(tiny_model, kind):
                     assert rel(r[3][-1], ref[3][-1]) <= 1e-2
     finally:
         graphs.GRAD_ENABLED = True
+
+
+@pytest.mark.parametrize("body_dtype", [torch.float32], indirect=True, ids=["fp32body"])
+def test_skipping_the_dead_uncond_reference_sample_preserves_the_edit(tiny_model, body_dtype):
+    """editor.SKIP_DEAD_UNCOND_REFERENCE evaluates the CFG batch without the unconditional reference sample (its output is overwritten by the
+    inversion latent, editor.py:375-377, and nobody attends to it).  The edited latent must not change beyond GEMM-shape rounding (fp32 body:
+    the batch-3 and batch-4 evaluations may use different cuBLAS / cuDNN kernels)."""
+    from geodiffuser_b200 import editor
+
+    try:
+        editor.SKIP_DEAD_UNCOND_REFERENCE = False
+        a = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=8)
+        editor.SKIP_DEAD_UNCOND_REFERENCE = True
+        b = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=8)
+    finally:
+        editor.SKIP_DEAD_UNCOND_REFERENCE = True
+    assert torch.equal(a[0], b[0])                                  # the reference sample is the inversion latent either way
+    p = psnr(b[1].float().cpu().numpy(), a[1].float().cpu().numpy())
+    print(f"edited latent, batch-3 vs batch-4 CFG pass: PSNR {p:.1f} dB")
+    assert p >= 60.0
