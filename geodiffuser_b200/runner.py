@@ -40,3 +40,118 @@ def run_requests(model, requests, rank=0, world_size=1, edit_fn=None):
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     return out, time.perf_counter() - t0
+
+
+# ---- experiment-folder format of the reference's batch driver ---------------------------------------------------------
+# ui_utils.save_exp / read_exp (:52-159) and large_scale_editor.py:133-178, 349-399: one edit = one folder holding input_image.png,
+# input_mask.png, depth.npy, transform.npy, image_shape.npy; results are written next to them (loss.pkl; the reference also decodes
+# result_ls.png through the VAE, which is outside this build, so the edited latents are stored as latents_ls.npy instead).
+EXP_FILES = ("input_image.png", "depth.npy", "input_mask.png", "transform.npy", "image_shape.npy", "background_image.png")
+SKIPPED_CATEGORIES = ("Rotation_2D", "Scaling")       # large_scale_editor.py:372
+
+
+def save_exp(folder, input_img, input_depth, input_mask, transform_in, h=512, w=512):
+    """ui_utils.save_exp (:52-112), the files the batch driver reads"""
+    import os
+    import cv2
+    import numpy as np
+
+    os.makedirs(folder, exist_ok=True)
+    cv2.imwrite(os.path.join(folder, "input_image.png"), np.asarray(input_img, np.uint8)[..., ::-1])
+    m = np.asarray(input_mask, np.float64)
+    m8 = (m * 255.0 if m.max() <= 1.0 else m).astype(np.uint8)
+    cv2.imwrite(os.path.join(folder, "input_mask.png"), np.repeat(m8[..., None], 3, -1) if m8.ndim == 2 else m8)
+    np.save(os.path.join(folder, "depth.npy"), np.asarray(input_depth))
+    np.save(os.path.join(folder, "transform.npy"), np.asarray(transform_in))
+    np.save(os.path.join(folder, "image_shape.npy"), np.array([int(h), int(w)]))
+
+
+def read_exp(d_path):
+    """ui_utils.read_exp (:118-159): {'<name>_png' | '<name>_npy': array or None, 'path_name': folder}"""
+    import os
+    import cv2
+    import numpy as np
+
+    folder = d_path if d_path.endswith("/") else d_path + "/"
+    out = {}
+    for f in EXP_FILES:
+        key, ext = f.split(".")
+        path = folder + f
+        val = None
+        if os.path.exists(path):
+            if ext == "png":
+                val = cv2.imread(path, cv2.IMREAD_UNCHANGED)
+                if val.ndim == 3:
+                    val = val[..., :3][..., ::-1].copy()
+            else:
+                val = np.load(path)
+        out[f"{key}_{ext}"] = val
+    if out["image_shape_npy"] is None:
+        out["image_shape_npy"] = np.array([512, 512])
+    out["path_name"] = folder
+    return out
+
+
+def exp_type_of_category(category):
+    """large_scale_editor.py:368-380: the folder's category decides the controller; two categories are skipped"""
+    if category in SKIPPED_CATEGORIES:
+        return None
+    return "geometry_remover" if category == "Removal" else "geometry_editor"
+
+
+def list_exp_folders(root):
+    """[(folder, exp_type)] under an experiment root `root/<Category>/<n>/` (check_if_exp_root layout), sorted like the reference's glob"""
+    import glob
+    import os
+
+    out = []
+    for cat_dir in sorted(glob.glob(os.path.join(root, "*/"))):
+        exp_type = exp_type_of_category(os.path.basename(os.path.normpath(cat_dir)))
+        if exp_type is None:
+            continue
+        for f in sorted(glob.glob(os.path.join(cat_dir, "*/"))):
+            if os.path.exists(os.path.join(f, "depth.npy")):
+                out.append((f, exp_type))
+    return out
+
+
+def request_from_exp(exp_dict, exp_type, seed=1234):
+    """perform_exp (:199-235): image_mask = input_mask[..., 0] / 255, depth, transform from the folder; the text / image encodings are
+    synthetic (CLIP and the VAE are outside this build)."""
+    import numpy as np
+    from . import editor
+
+    mask = exp_dict["input_mask_png"]
+    mask = (mask[..., 0] if mask.ndim == 3 else mask) / 255.0
+    size = int(mask.shape[0])
+    text, uncond, x0 = editor.synthetic_embeddings(seed, "cpu", size)
+    return dict(depth=np.asarray(exp_dict["depth_npy"], np.float64), image_mask=mask.astype(np.float64),
+                transform_in=torch.tensor(np.asarray(exp_dict["transform_npy"])).float(), text_embeddings=text, uncond_embeddings=uncond, x0=x0,
+                edit_type=exp_type)
+
+
+def run_exp_on_folder_single(model, exp_folder, exp_type, **kw):
+    """large_scale_editor.py:349-365: read the folder, edit, write the results into it.  Returns the edited latents (host)."""
+    import pickle
+    import numpy as np
+    from . import editor
+
+    exp = read_exp(exp_folder)
+    req = request_from_exp(exp, exp_type)
+    staged, _ = editor.stage_inputs(req["depth"], req["image_mask"], req["text_embeddings"], req["uncond_embeddings"], req["x0"], model.device)
+    latents, log = editor.run_edit(model, staged, req["transform_in"], exp_type, return_log=True, **kw)
+    out = latents.float().cpu().numpy()
+    np.save(exp["path_name"] + "latents_ls.npy", out)
+    with open(exp["path_name"] + "loss.pkl", "wb") as f:
+        pickle.dump(log, f)
+    return out
+
+
+def run_exp_root(model, root, rank=0, world_size=1, **kw):
+    """the reference's folder loop (:392-399), sharded round-robin over ranks.  Returns the folders this rank served."""
+    folders = list_exp_folders(root)
+    done = []
+    for i in shard_round_robin(len(folders), rank, world_size):
+        run_exp_on_folder_single(model, folders[i][0], folders[i][1], **kw)
+        done.append(folders[i][0])
+    return done

@@ -87,3 +87,33 @@ def test_unet_topology_is_sd15():
     assert sum(p.numel() for p in u.parameters()) == 859520964    # SD-1.x UNet parameter count
     heads = {m.to_q.in_features // m.heads for _, m in u._attention_modules()}
     assert heads == {40, 80, 160}
+
+
+def test_experiment_folder_format_round_trip(tmp_path):
+    """ui_utils.save_exp / read_exp layout: category folders decide the controller, two categories are skipped, the request read
+    back from a folder equals the one written, and the round-robin shards cover every folder exactly once."""
+    import numpy as np
+    from geodiffuser_b200 import runner, synth
+
+    root = tmp_path / "exp_root"
+    written = {}
+    for cat, kind in (("Translation_2D", "translate2d"), ("Rotation_3D", "rotate3d"), ("Removal", "remove"), ("Scaling", "translate2d")):
+        for n in (1, 2):
+            image, depth, mask, T = synth.edit_inputs(kind)
+            folder = str(root / cat / str(n))
+            runner.save_exp(folder, image, depth, mask, T.numpy())
+            written[folder + "/"] = (image, depth, mask, T.numpy())
+    folders = runner.list_exp_folders(str(root))
+    assert len(folders) == 6 and all("Scaling" not in f for f, _ in folders)
+    assert {t for f, t in folders if "Removal" in f} == {"geometry_remover"}
+    assert {t for f, t in folders if "Removal" not in f} == {"geometry_editor"}
+    f, t = folders[0]
+    exp = runner.read_exp(f)
+    image, depth, mask, T = written[f]
+    assert np.array_equal(exp["input_image_png"], image) and exp["background_image_png"] is None
+    assert np.array_equal(exp["image_shape_npy"], [512, 512])
+    req = runner.request_from_exp(exp, t)
+    assert np.array_equal(req["image_mask"], mask) and np.array_equal(req["depth"], depth)
+    assert np.allclose(req["transform_in"].numpy(), T) and req["x0"].shape == (1, 4, 64, 64)
+    shards = [runner.shard_round_robin(len(folders), r, 4) for r in range(4)]
+    assert sorted(i for s in shards for i in s) == list(range(6))
