@@ -28,6 +28,7 @@ SIGNATURES = {
     "gd_attn_sm100_config": [I],
     "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, I, I, I, I, P, P, P],
     "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P],
+    "gd_attn_bwd_dk_split": [P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I, I, F, P],
     "gd_attn_bwd_sm100": [P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, F, P],
     "gd_cast_f32_to_bf16": [P, P, L, P],
     "gd_attn_probs": [P, P, P, P, I, I, I, I, I, F, P, I, P],
@@ -42,12 +43,16 @@ SIGNATURES = {
     "gd_latent_update": [P, P, P, I, F, L, P, P],
     "gd_norm_rescale": [P, L, F, P, P],
     "gd_latent_blend": [P, P, P, I, I, L, P, P],
+    "gd_group_norm_nhwc_fwd": [P, P, P, I, I, I, I, I, F, I, P, L, P, P, P],
+    "gd_group_norm_nhwc_bwd": [P, P, P, P, I, P, I, I, I, I, I, P, L, P, P],
+    "gd_group_norm_nhwc_workspace": [I, I, I, I],
 }
 
 _LIB = None
 HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
 LAUNCHES = 0  # CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
-KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2}  # every other entry point launches one
+KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2, "gd_attn_bwd_dk_split": 2,
+                    "gd_group_norm_nhwc_fwd": 2, "gd_group_norm_nhwc_bwd": 2, "gd_group_norm_nhwc_workspace": 0}  # every other entry point launches one
 
 
 class GeoDiffuserB200Error(RuntimeError):

@@ -173,6 +173,7 @@ struct AttnBwdParams {
     float* out;                             // (H, n_outer, d) fp32
     int H, n_outer, n_inner, d;
     float scale;
+    int chunk;                              // MODE 1 only: inner (query) tiles per blockIdx.z; out is then (gridDim.z, H, n_outer, d) partial sums
 };
 
 template <int DPAD, int MODE>
@@ -196,11 +197,15 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
 
     for (int i = tid; i < (6 * 64 * LD) / 8; i += ATT_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    const int nT = (ni + 63) / 64;
+    // dK walks the queries: with Nk = 77 there are only 2 outer tiles per head, so the query range is split over blockIdx.z
+    // (16 CTAs walking 4096 queries serially took 370 us per launch) and the partial sums are added in a fixed order afterwards
+    const int nT_all = (ni + 63) / 64;
+    const int jt0 = (MODE == 1 && p.chunk > 0) ? blockIdx.z * p.chunk : 0;
+    const int nT = (MODE == 1 && p.chunk > 0) ? min(nT_all, jt0 + p.chunk) : nT_all;
     load_tile_async<ATT_THREADS>(X1, LD, x1g, d, d, min(64, no - o0), tid);
     load_tile_async<ATT_THREADS>(X2, LD, x2g, d, d, min(64, no - o0), tid);
-    load_tile_async<ATT_THREADS>(Y1, LD, y1g, d, d, min(64, ni), tid);
-    load_tile_async<ATT_THREADS>(Y2, LD, y2g, d, d, min(64, ni), tid);
+    load_tile_async<ATT_THREADS>(Y1, LD, y1g + (long)jt0 * 64 * d, d, d, min(64, ni - jt0 * 64), tid);
+    load_tile_async<ATT_THREADS>(Y2, LD, y2g + (long)jt0 * 64 * d, d, d, min(64, ni - jt0 * 64), tid);
     cp_async_commit();
 
     float acc[DPAD / 8][4];
@@ -221,8 +226,8 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
             }
     }
 
-    for (int jt = 0; jt < nT; ++jt) {
-        const int st = jt & 1;
+    for (int jt = jt0; jt < nT; ++jt) {
+        const int st = (jt - jt0) & 1;
         if (jt + 1 < nT) {
             const int i1 = (jt + 1) * 64;
             load_tile_async<ATT_THREADS>(Y1 + (st ^ 1) * 64 * LD, LD, y1g + (long)i1 * d, d, d, min(64, ni - i1), tid);
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
             }
         __syncthreads();
     }
-    float* og = p.out + (long)h * no * d;
+    float* og = p.out + ((long)blockIdx.z * p.H + h) * no * d;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         if (orow[r] >= no) continue;
@@ -335,6 +340,18 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
     if (i < n) dst[i] = __float2bfloat16_rn(src[i]);
 }
 
+// out[i] = sum_z part[z, i] in ascending z (fixed order: deterministic)
+__global__ void sum_partials_kernel(const float* __restrict__ part, int Z, long n, float* __restrict__ out) {
+    const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    float4 a = *reinterpret_cast<const float4*>(part + i);
+    for (int z = 1; z < Z; ++z) {
+        const float4 b = *reinterpret_cast<const float4*>(part + (long)z * n + i);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    *reinterpret_cast<float4*>(out + i) = a;
+}
+
 template <int DPAD> static int launch_fwd(const AttnFwdParams& p, cudaStream_t st) {
     const size_t smem = (size_t)5 * 64 * (DPAD + 8) * sizeof(bf16);
     static bool configured = false;
@@ -349,7 +366,7 @@ template <int DPAD> static int launch_fwd(const AttnFwdParams& p, cudaStream_t s
     return GD_OK;
 }
 
-template <int DPAD, int MODE> static int launch_bwd(const AttnBwdParams& p, cudaStream_t st) {
+template <int DPAD, int MODE> static int launch_bwd(const AttnBwdParams& p, cudaStream_t st, int Z = 1) {
     const size_t smem = (size_t)6 * 64 * (DPAD + 8) * sizeof(bf16);
     static bool configured = false;
     if (!configured) {
@@ -357,7 +374,7 @@ template <int DPAD, int MODE> static int launch_bwd(const AttnBwdParams& p, cuda
         if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    dim3 grid(ceil_div(p.n_outer, 64), p.H);
+    dim3 grid(ceil_div(p.n_outer, 64), p.H, Z);
     flash_bwd_mma_kernel<DPAD, MODE><<<grid, ATT_THREADS, smem, st>>>(p);
     GD_CHECK_LAUNCH();
     return GD_OK;
@@ -412,7 +429,7 @@ int gd_attn_bwd(int mode, const void* q, const void* k, const void* v, const voi
     GD_CHECK_ARG((extra == nullptr) == (rowmap == nullptr));
     AttnBwdParams p;
     p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.out = out;
-    p.H = H; p.d = d; p.scale = scale;
+    p.H = H; p.d = d; p.scale = scale; p.chunk = 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (mode == 0) {
         p.x1 = (const bf16*)q; p.x2 = (const bf16*)d_o; p.y1 = (const bf16*)k; p.y2 = (const bf16*)v; p.n_outer = N; p.n_inner = Nk;
@@ -426,6 +443,36 @@ int gd_attn_bwd(int mode, const void* q, const void* k, const void* v, const voi
         if (d <= 160) return launch_bwd<160, 1>(p, st);
     }
     return set_error(GD_ERR_UNSUPPORTED, "head_dim %d > 160", d);
+}
+
+// dK as gd_attn_bwd mode 1, with the query range split over the grid: workspace (>= splits * H * Nk * d floats, H*Nk*d % 4 == 0) receives
+// the per-split partial sums, which are then added in ascending order (deterministic).  splits <= 1 or no workspace: same as mode 1.
+int gd_attn_bwd_dk_split(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
+                         const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* dk, float* workspace,
+                         int splits, int H, int N, int Nk, int d, float scale, void* stream) {
+    const int nT = (N + 63) / 64;
+    if (splits > nT) splits = nT;
+    if (!workspace || splits <= 1 || ((long)H * Nk * d) % 4 != 0)
+        return gd_attn_bwd(1, q, k, v, d_o, lse, delta, extra, extra_scale, rowmap, ex_ld, M, dk, H, N, Nk, d, scale, stream);
+    GD_CHECK_ARG(q && k && v && d_o && lse && delta && dk && H > 0 && N > 0 && Nk > 0 && d > 0 && (d % 8) == 0);
+    GD_CHECK_ARG((extra == nullptr) == (rowmap == nullptr));
+    AttnBwdParams p;
+    p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.out = workspace;
+    p.H = H; p.d = d; p.scale = scale;
+    p.chunk = (nT + splits - 1) / splits;
+    const int Z = (nT + p.chunk - 1) / p.chunk;
+    p.x1 = (const bf16*)k; p.x2 = (const bf16*)v; p.y1 = (const bf16*)q; p.y2 = (const bf16*)d_o; p.n_outer = Nk; p.n_inner = N;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+    if (d <= 48) rc = launch_bwd<48, 1>(p, st, Z);
+    else if (d <= 80) rc = launch_bwd<80, 1>(p, st, Z);
+    else if (d <= 160) rc = launch_bwd<160, 1>(p, st, Z);
+    else return set_error(GD_ERR_UNSUPPORTED, "head_dim %d > 160", d);
+    if (rc != GD_OK) return rc;
+    const long n = (long)H * Nk * d;
+    sum_partials_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(workspace, Z, n, dk);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
 }
 
 int gd_cast_f32_to_bf16(const float* src, void* dst, long n, void* stream) {

@@ -10,7 +10,7 @@ mkdir -p _obj
 pids=""
 # geometry.cu: bit-exact integer artefacts behind an fp32 pipeline -> no FMA contraction
 $NVCC $COMMON -fmad=false -c geometry.cu -o _obj/geometry.o 2> _obj/geometry.log & pids="$pids $!"
-for f in attention_mma corr_gemm losses elementwise attention_sm100; do
+for f in attention_mma corr_gemm losses elementwise attention_sm100 body_norm; do
     if [ -f $f.cu ]; then
         $NVCC $COMMON -c $f.cu -o _obj/$f.o 2> _obj/$f.log & pids="$pids $!"
     fi

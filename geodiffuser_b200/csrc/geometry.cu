@@ -282,6 +282,61 @@ __global__ void splat_composite_kernel(const TIn* __restrict__ src, long sb, lon
     stf<TOut>(out + (long)b * ob + (long)p * op + (long)c * oc, w);
 }
 
+// Row form of the composite for channel-fastest sources sharing one index (the per-layer query warp: src (B=heads, P, C=head_dim), Bi = 1):
+// one warp per output pixel.  The K blend weights cum_k * alpha_k depend only on the pixel, so they are formed once per warp -- same IEEE
+// operations in the same order as splat_composite_kernel, hence bit-identical results -- instead of once per (head, channel); the lanes
+// then sweep the B*C feature values of that pixel (rows of C contiguous elements per head -> coalesced gathers).
+template <typename TIn, typename TOut>
+__global__ void splat_composite_rows_kernel(const TIn* __restrict__ src, long sb, long sp, const int* __restrict__ idx,
+                                            const float* __restrict__ dist2, int B, int P, int C, int K, float r2, float tau,
+                                            const float* __restrict__ blend, int post, TOut* __restrict__ out, long ob, long op) {
+    const int lane = threadIdx.x & 31;
+    const int p = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (p >= P) return;
+    int n = -1;
+    float a = 0.0f;
+    if (lane < K) {
+        n = idx[(long)p * K + lane];
+        if (n >= 0) {
+            a = __fsub_rn(1.0f, __fsqrt_rn(fminf(fmaxf(__fdiv_rn(dist2[(long)p * K + lane], r2), 1e-3f), 1.0f)));
+            if (tau != 1.0f) a = powf(a, tau);
+        }
+    }
+    // weights in slot order; empty slots (n < 0) are skipped by the reference loop: weight 0 is NOT the same as skipping only for the
+    // accumulate of a -0.0 / NaN product, so keep the skip by compacting valid slots to the front
+    const unsigned valid = __ballot_sync(0xffffffffu, n >= 0);
+    float cum = 1.0f, w_mine = 0.0f;
+    int n_mine = -1, cnt = 0;
+    for (int k = 0; k < K; ++k) {
+        const float ak = __shfl_sync(0xffffffffu, a, k);
+        const int nk = __shfl_sync(0xffffffffu, n, k);
+        if (!((valid >> k) & 1u)) continue;
+        const float wk = __fmul_rn(cum, ak);
+        cum = __fmul_rn(cum, __fsub_rn(1.0f, ak));
+        if (lane == cnt) { w_mine = wk; n_mine = nk; }
+        ++cnt;
+    }
+    const float m = blend ? blend[p] : 0.0f;
+    const int total = B * C;
+    for (int e0 = 0; e0 < total; e0 += 32) {      // uniform trip count: every lane takes part in the shuffles
+        const int e = e0 + lane;
+        const bool on = e < total;
+        const int b = on ? e / C : 0, c = on ? e - b * C : 0;
+        const TIn* s = src + (long)b * sb + c;
+        float acc = 0.0f;
+        for (int k = 0; k < cnt; ++k) {
+            const float wk = __shfl_sync(0xffffffffu, w_mine, k);
+            const int nk = __shfl_sync(0xffffffffu, n_mine, k);
+            acc = __fadd_rn(acc, __fmul_rn(wk, ldf<TIn>(s + (long)nk * sp)));
+        }
+        if (!on) continue;
+        float w = __half2float(__float2half_rn(acc));
+        if (blend) w = __fadd_rn(__fmul_rn(ldf<TIn>(s + (long)p * sp), __fsub_rn(1.0f, m)), __fmul_rn(m, w));
+        if (post == 1) w = bin05(w);
+        stf<TOut>(out + (long)b * ob + (long)p * op + c, w);
+    }
+}
+
 // ---- amodal mesh coverage -----------------------------------------------------------------------
 __device__ __forceinline__ float edge_fn(float px, float py, float ax, float ay, float bx, float by) {
     return __fsub_rn(__fmul_rn(__fsub_rn(px, ax), __fsub_rn(by, ay)), __fmul_rn(__fsub_rn(py, ay), __fsub_rn(bx, ax)));
@@ -433,6 +488,18 @@ int gd_splat_composite(const void* src, int src_dtype, int layout, const int* id
     const long total = (long)B * P * C;
     const long sb = (long)P * C, sp = layout ? C : 1, sc = layout ? 1 : P;
     cudaStream_t st = (cudaStream_t)stream;
+    if (layout == 1 && Bi == 1 && K <= 32 && (long)B * C >= 32) {   // per-layer query warp: one warp per pixel, weights formed once
+        const int gr = ceil_div((long)P * 32, 256);
+#define GD_LAUNCH_ROWS(TI, TO) \
+    splat_composite_rows_kernel<TI, TO><<<gr, 256, 0, st>>>((const TI*)src, sb, sp, idx, dist2, B, P, C, K, r2, tau, blend_mask, post, (TO*)out, sb, sp)
+        if (src_dtype == 0 && out_dtype == 0) GD_LAUNCH_ROWS(float, float);
+        else if (src_dtype == 0 && out_dtype == 1) GD_LAUNCH_ROWS(float, __nv_bfloat16);
+        else if (src_dtype == 1 && out_dtype == 0) GD_LAUNCH_ROWS(__nv_bfloat16, float);
+        else GD_LAUNCH_ROWS(__nv_bfloat16, __nv_bfloat16);
+#undef GD_LAUNCH_ROWS
+        GD_CHECK_LAUNCH();
+        return GD_OK;
+    }
     const int g = ceil_div(total, 256);
 #define GD_LAUNCH_COMPOSITE(TI, TO)                                                                                         \
     splat_composite_kernel<TI, TO><<<g, 256, 0, st>>>((const TI*)src, sb, sp, sc, idx, dist2, Bi, B, P, C, K, r2, tau, blend_mask, \

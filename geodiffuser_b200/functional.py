@@ -288,8 +288,11 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
         dk = None
         if spec.is_cross and spec.kind == "edit":
             dk_e = torch.empty(h, Nk, d, device=dev, dtype=torch.float32)
-            call("gd_attn_bwd", 1, ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dk_e), h, N, Nk, d, float(spec.scale), stream())
+            # Nk = 77 -> two key tiles per head: split the query walk so the grid fills the 148 SMs (fixed-order partial sums)
+            splits = max(1, min((N + 63) // 64, (2 * 148) // (h * ((Nk + 63) // 64))))
+            ws = torch.empty(splits, h, Nk, d, device=dev, dtype=torch.float32) if splits > 1 else None
+            call("gd_attn_bwd_dk_split", ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
+                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dk_e), ptr(ws), splits, h, N, Nk, d, float(spec.scale), stream())
             dk = torch.zeros(k_shape, device=dev, dtype=k_dtype)
             dk[ce0 * h:ce1 * h] = dk_e.to(k_dtype)
         return dq, dk, None, None

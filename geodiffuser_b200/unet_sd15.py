@@ -20,6 +20,8 @@ import torch.nn.functional as F
 
 import os
 
+from .body_ops import group_norm_act
+
 BODY_CHANNELS_LAST = os.environ.get("GD_BODY_NCHW", "0") != "1"   # bf16 body layout: NHWC (cuDNN's native tensor-core layout) unless overridden
 
 
@@ -113,7 +115,7 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, context):
         b, c, h, w = x.shape
         res = x
-        x = self.proj_in(self.norm(x))
+        x = self.proj_in(group_norm_act(self.norm, x))
         x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
         for blk in self.transformer_blocks:
             x = blk(x, context)
@@ -132,9 +134,9 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
     def forward(self, x, temb):
-        h = self.conv1(F.silu(self.norm1(x)))
+        h = self.conv1(group_norm_act(self.norm1, x, silu=True))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
-        h = self.conv2(F.silu(self.norm2(h)))
+        h = self.conv2(group_norm_act(self.norm2, h, silu=True))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         return x + h
@@ -292,7 +294,7 @@ class UNet2DConditionModel(nn.Module):
         x = self.mid_block(x, temb, encoder_hidden_states)
         for blk in self.up_blocks:
             x = blk(x, skips, temb, encoder_hidden_states)
-        x = self.conv_out(F.silu(self.conv_norm_out(x)))
+        x = self.conv_out(group_norm_act(self.conv_norm_out, x, silu=True))
         return {"sample": x}
 
 

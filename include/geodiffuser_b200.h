@@ -86,6 +86,13 @@ int gd_attn_bwd(int mode, const void* q, const void* k, const void* v, const voi
                 const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* out, int H, int N, int Nk,
                 int d, float scale, void* stream);
 
+/* dK exactly as gd_attn_bwd mode 1, but with the query range split `splits` ways across the grid (cross layers: Nk = 77 gives only two
+ * 64-key tiles per head, so one CTA per tile would walk all N queries serially).  workspace: >= splits * H * Nk * d floats; the partial
+ * sums are added in ascending split order, so the result is deterministic.  splits <= 1 or workspace == NULL falls back to mode 1. */
+int gd_attn_bwd_dk_split(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
+                         const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* dk, float* workspace,
+                         int splits, int H, int N, int Nk, int d, float scale, void* stream);
+
 /* Same operands and result as gd_attn_bwd mode 0 (dQ), tcgen05 / TMEM / TMA kernel for the self-attention levels:
  * N == Nk, N % 128 == 0, d in {40, 80}; extra rows (if any) 16-byte aligned (ex_ld % 4 == 0). */
 int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
@@ -148,6 +155,17 @@ int gd_norm_rescale(float* x, long n, float target_norm, float* norm_out, void* 
 
 /* editor.py:393-399: out = a (1 - m) + m b, m optionally binarised (> 0.5). */
 int gd_latent_blend(const float* a, const float* b, const float* mask, int hw, int binarize, long n, float* out, void* stream);
+
+/* ---- caller-side fused op (NOT part of the reference surface; SURVEY 8 row A14 leaves the UNet body to stock torch) -------------
+ * GroupNorm (+ SiLU) on channels-last bf16 activations: torch's CUDA group_norm round-trips through NCHW (2 layout copies + 4 kernels
+ * per norm, 61 norms per UNet evaluation), which hides the path behind the body.  x, y, dy, dx (B, HW, C) bf16, C % 8 == 0, G <= 32;
+ * gamma / beta (C) bf16 or fp32; stats (B, G, 2) = (mean, rstd) saved for the backward; workspace >= gd_group_norm_nhwc_workspace()
+ * floats.  The backward returns dx only (the body's weights are frozen in the edit loop, optimization.py:213-219). */
+int gd_group_norm_nhwc_fwd(const void* x, const void* gamma, const void* beta, int w_is_bf16, int B, int HW, int C, int G, float eps, int silu,
+                           float* workspace, long workspace_floats, float* stats, void* y, void* stream);
+int gd_group_norm_nhwc_bwd(const void* x, const void* dy, const void* gamma, const void* beta, int w_is_bf16, const float* stats, int B, int HW,
+                           int C, int G, int silu, float* workspace, long workspace_floats, void* dx, void* stream);
+int gd_group_norm_nhwc_workspace(int B, int HW, int C, int G);
 
 #ifdef __cplusplus
 }

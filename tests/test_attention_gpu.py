@@ -120,3 +120,48 @@ def test_plain_attention_outside_window_and_counters():
         assert (c.cur_att_layer, c.cur_step) == (1, 48)
         c(q, k, v, False, "up", transform_coords=geo["coords"], scale=d ** -0.5)
         assert (c.cur_att_layer, c.cur_step) == (0, 49)
+
+
+@pytest.mark.parametrize("N,Nk,d,M,splits", [(4096, 77, 40, 300, 18), (1024, 77, 80, 0, 16), (256, 77, 160, 0, 4), (200, 77, 40, 17, 3)])
+@pytest.mark.timeout(120)
+def test_cross_layer_dk_split_matches_unsplit_and_fp32(N, Nk, d, M, splits):
+    """dK of the cross layers with the query walk split over the grid (gd_attn_bwd_dk_split) == the one-CTA-per-key-tile kernel (mode 1)
+    up to the fp32 summation order, == the fp32 evaluation within the path's tolerance, and bit-identical from run to run."""
+    from geodiffuser_b200 import _lib
+    from geodiffuser_b200._lib import call, ptr, stream
+
+    H = 8
+    g = torch.Generator(device="cuda").manual_seed(N + d + M)
+    q, do = [(torch.randn(H, N, d, device="cuda", generator=g) * s).bfloat16() for s in (1.5, 1.0)]
+    k, v = [(torch.randn(H, Nk, d, device="cuda", generator=g) * 1.5).bfloat16() for _ in range(2)]
+    scale = d ** -0.5
+    s = torch.einsum("hnd,hkd->hnk", q.float(), k.float()) * scale
+    p = torch.softmax(s, -1)
+    L = torch.logsumexp(s, -1).contiguous()
+    dp = torch.einsum("hnd,hkd->hnk", do.float(), v.float())
+    ld = (Nk + 7) // 8 * 8
+    extra = rowmap = dl = None
+    if M:
+        rows = torch.randperm(N, device="cuda", generator=g)[:M].sort().values.int()
+        rowmap = torch.full((N,), -1, device="cuda", dtype=torch.int32)
+        rowmap[rows.long()] = torch.arange(M, device="cuda", dtype=torch.int32)
+        extra = torch.randn(H, M, ld, device="cuda", generator=g) * 0.05
+        dl = torch.full((1,), 0.7, device="cuda")
+        dp[:, rows.long(), :] += 0.7 * extra[:, :, :Nk]
+    delta = (p * dp).sum(-1).contiguous()
+    ref = torch.einsum("hnk,hnd->hkd", p * (dp - delta[..., None]), q.float()) * scale
+    dk0 = torch.full((H, Nk, d), float("nan"), device="cuda")
+    call("gd_attn_bwd", 1, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dk0), H, N, Nk, d,
+         float(scale), stream())
+    outs = []
+    for _ in range(2):
+        dk = torch.full((H, Nk, d), float("nan"), device="cuda")
+        ws = torch.full((splits, H, Nk, d), float("nan"), device="cuda")
+        call("gd_attn_bwd_dk_split", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dk), ptr(ws),
+             splits, H, N, Nk, d, float(scale), stream())
+        torch.cuda.synchronize()
+        outs.append(dk)
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1])
+    assert relerr(outs[0].cpu().numpy(), dk0.cpu().numpy()) <= 1e-5
+    assert relerr(outs[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2

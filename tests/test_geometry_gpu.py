@@ -143,3 +143,26 @@ def test_morph_matches_conv():
     di = (torch.nn.functional.conv2d(t, k5, padding=2) >= 1) * 1.0
     np.testing.assert_array_equal(G.torch_erode(t.cuda(), 3).cpu().numpy(), er.numpy())
     np.testing.assert_array_equal(G.torch_dilate(t.cuda(), 5).cpu().numpy(), di.numpy())
+
+
+@pytest.mark.parametrize("kind,S,B,C,dt", [("rotate3d", 64, 8, 40, torch.bfloat16), ("translate2d", 32, 8, 80, torch.bfloat16),
+                                           ("rotate3d", 16, 3, 18, torch.float32), ("translate2d", 64, 8, 40, torch.float32)])
+def test_query_warp_rows_kernel_bit_exact_vs_pixel_kernel_and_oracle(geo, kind, S, B, C, dt):
+    """the per-layer query warp (one warp per pixel, blend weights formed once per pixel) == the one-thread-per-element composite on the
+    same data, bit for bit, with and without the M_edit blend; and == the CPU oracle's composite"""
+    from geodiffuser_b200 import geometry as G
+    from oracle import geodiff_oracle as O
+
+    cS = G.reshape_transform_coords(geo[kind]["coords"][None], in_mat_shape=(1, 1, S, S))
+    idx, _, d2 = G.splat_index(cS)
+    g = torch.Generator(device="cuda").manual_seed(S + C)
+    src = torch.randn(B, S * S, C, device="cuda", generator=g).to(dt)
+    blend = torch.rand(S * S, device="cuda", generator=g)
+    nchw = src.permute(0, 2, 1).reshape(B, C, S, S).contiguous()
+    for bm in (None, blend):
+        rows = G.splat_composite(src, idx, d2, channels_last=True, blend_mask=bm, out_dtype=dt)
+        pix = G.splat_composite(nchw, idx, d2, channels_last=False, blend_mask=bm, out_dtype=dt)
+        assert torch.equal(rows, pix.reshape(B, C, S * S).permute(0, 2, 1))
+    ref = O.splat_composite(nchw[:1].float().cpu().numpy(), idx.cpu().numpy(), d2.cpu().numpy())
+    got = G.splat_composite(src, idx, d2, channels_last=True, out_dtype=torch.float32)
+    assert relerr(got[:1].permute(0, 2, 1).reshape(1, C, S, S).cpu().numpy(), ref) <= 1e-3   # one fp16 ulp (see make_golden)
