@@ -23,22 +23,23 @@ SIGNATURES = {
     "gd_splat_composite": [P, I, I, P, P, I, I, I, I, I, F, F, P, I, P, I, P],
     "gd_mesh_mask": [P, P, I, I, F, P, P],
     "gd_morph": [P, I, I, I, I, I, P, P],
-    "gd_attn_fwd_generic": [P, P, P, P, P, I, I, I, I, I, F, P],
-    "gd_attn_fwd_sm100": [P, P, P, P, P, I, I, I, I, I, F, P],
+    "gd_attn_fwd_generic": [P, P, P, P, P, P, I, I, I, I, I, F, P, I, P],
+    "gd_attn_fwd_sm100": [P, P, P, P, P, P, I, I, I, I, I, F, P, I, P],
     "gd_attn_sm100_config": [I],
-    "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, I, I, I, I, P, P, P],
-    "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P],
-    "gd_attn_bwd_dk_split": [P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I, I, F, P],
-    "gd_attn_bwd_sm100": [P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, F, P],
+    "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, P, I, I, I, I, P, P, P],
+    "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P, I, P],
+    "gd_attn_bwd_dk_split": [P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I, I, F, P, I, P],
+    "gd_attn_bwd_sm100": [P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, F, P, I, P],
     "gd_cast_f32_to_bf16": [P, P, L, P],
-    "gd_attn_probs": [P, P, P, P, I, I, I, I, I, F, P, I, P],
+    "gd_attn_probs": [P, P, P, P, I, I, I, I, I, F, P, I, P, P],
     "gd_corr_max_partial": [P, P, I, I, I, I, I, P, P, P, P],
     "gd_attn_l1_losses": [P, P, P, P, P, P, P, F, F, F, F, F, I, I, I, P, P, I, P],
     "gd_removal_finalize": [P, I, I, I, I, P, P, P, F, P, P, I, I, I, P, P, P, P, P, P],
     "gd_loss_reduce": [P, I, P, I, P, P, P, F, P, P, P],
     "gd_amodal_knn": [P, I, P, P, P, P],
     "gd_amodal_target": [P, P, P, P, P, I, I, I, P, P, P],
-    "gd_blend_rows": [P, P, P, P, I, I, I, P, I, P],
+    "gd_blend_rows": [P, P, P, P, I, I, I, P, I, P, P],
+    "gd_splat_composite_rows": [P, I, P, P, P, I, I, I, I, F, F, P, I, P, I, P, P],
     "gd_ddim_step": [P, P, P, I, F, F, F, F, F, L, P, P, P],
     "gd_latent_update": [P, P, P, I, F, L, P, P],
     "gd_norm_rescale": [P, L, F, P, P],
@@ -131,9 +132,25 @@ def host_f32(values):
 
 
 def ptr_array(tensors):
-    """host array of device pointers"""
-    arr = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    """host array of device pointers (None -> NULL)"""
+    arr = (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
     return arr
+
+
+def base_ptr(t):
+    """device pointer of the first element of a (possibly strided) CUDA tensor view: for the slab arguments, whose strides travel separately"""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GeoDiffuserB200Error("expected a CUDA tensor: geodiffuser_b200 has no CPU path")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def host_longs(values):
+    """host long array (element strides of slab arguments); None -> NULL (contiguous)"""
+    if values is None:
+        return None
+    return (ctypes.c_long * len(values))(*[int(v) for v in values])
 
 
 def stream():

@@ -24,6 +24,12 @@ from . import geometry
 # the random-init UNet used here has plain nn.Linear projections: same call convention as diffusers with the PEFT backend
 USE_PEFT_BACKEND = True
 
+# The processors hand q / k / v to the controller as functional.ProjView (the projection output (B, N, H*d) presented with the reference's
+# (B*H, N, d) shape) and get the attention output back in projection layout: the kernels address the head slabs in place, so the
+# reference's head_to_batch_dim / batch_to_head_dim copies (attention_processors.py:201-203, 225) disappear.  False = the reference's
+# literal tensor layout through the same kernels (tests run both).
+PROJECTION_LAYOUT = True
+
 
 def register_attention_control_diffusers(model, controller, transform_coords=None):
     attn_procs = {}
@@ -75,18 +81,24 @@ def _project_qkv(attn, hidden_states, encoder_hidden_states, attention_mask, tem
         encoder_hidden_states = attn.norm_encoder_hidden_states(encoder_hidden_states)
     key = attn.to_k(encoder_hidden_states, *args)
     value = attn.to_v(encoder_hidden_states, *args)
+    if PROJECTION_LAYOUT and query.is_cuda:
+        h = attn.heads
+        return Fn.ProjView(query, h), Fn.ProjView(key, h), Fn.ProjView(value, h), is_cross, shape4, args
     return attn.head_to_batch_dim(query), attn.head_to_batch_dim(key), attn.head_to_batch_dim(value), is_cross, shape4, args
 
 
-def _finish(attn, hidden_states, residual, shape4, args):
-    hidden_states = attn.batch_to_head_dim(hidden_states)
+def _finish(attn, hidden_states, residual, shape4, args, proj=False):
+    if not proj:
+        hidden_states = attn.batch_to_head_dim(hidden_states)
     hidden_states = attn.to_out[0](hidden_states, *args)
     hidden_states = attn.to_out[1](hidden_states)
     if shape4 is not None:
         hidden_states = hidden_states.transpose(-1, -2).reshape(shape4)
     if attn.residual_connection:
         hidden_states = hidden_states + residual
-    return hidden_states / attn.rescale_output_factor
+    if attn.rescale_output_factor != 1.0:      # x / 1.0 == x: not worth a kernel launch per layer
+        hidden_states = hidden_states / attn.rescale_output_factor
+    return hidden_states
 
 
 class VanillaAttentionProcessor:
@@ -98,7 +110,7 @@ class VanillaAttentionProcessor:
         if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
             raise NotImplementedError("VanillaAttentionProcessor is forward-only (DDIM inversion / final reset, editor.py:698)")
         hidden_states = Fn.plain_attention(q, k, v, attn.scale, attn.heads)
-        return _finish(attn, hidden_states, residual, shape4, args)
+        return _finish(attn, hidden_states, residual, shape4, args, isinstance(q, Fn.ProjView))
 
 
 class EditProcessor:
@@ -122,7 +134,7 @@ class EditProcessor:
             if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
                 raise NotImplementedError("perform_edit=False is forward-only")
             hidden_states = Fn.plain_attention(q, k, v, attn.scale, attn.heads)
-        return _finish(attn, hidden_states, residual, shape4, args)
+        return _finish(attn, hidden_states, residual, shape4, args, isinstance(q, Fn.ProjView))
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -24,10 +24,13 @@ struct AttnFwdParams {
     const bf16* q[ATT_MAXG];
     const bf16* k[ATT_MAXG];
     const bf16* v[ATT_MAXG];
-    float* o[ATT_MAXG];
+    float* o[ATT_MAXG];        // (H, N, d) fp32 contiguous, or NULL
     float* lse[ATT_MAXG];
+    void* os[ATT_MAXG];        // strided output (row stride os_rs, head stride os_hs; bf16 or fp32), or NULL
     int G, H, N, Nk, d;
     float scale;
+    long q_rs, q_hs, kv_rs, kv_hs, os_rs, os_hs;   // element strides of one (H, N, d) slab: token row, head
+    int os_bf16;
 };
 
 // grid (ceil(N/64), H, G); 4 warps x 16 query rows; key tiles of 64, double-buffered with cp.async
@@ -41,18 +44,18 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_fwd_mma_kernel(const AttnFw
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * 64;
     const int N = p.N, Nk = p.Nk, d = p.d;
-    const bf16* Qg = p.q[g] + ((long)h * N + q0) * d;
-    const bf16* Kg = p.k[g] + (long)h * Nk * d;
-    const bf16* Vg = p.v[g] + (long)h * Nk * d;
+    const bf16* Qg = p.q[g] + (long)h * p.q_hs + (long)q0 * p.q_rs;
+    const bf16* Kg = p.k[g] + (long)h * p.kv_hs;
+    const bf16* Vg = p.v[g] + (long)h * p.kv_hs;
 
     // zero everything once so the d..DPAD pad columns (never written by the tile loads) are 0
     for (int i = tid; i < (5 * 64 * LD) / 8; i += ATT_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
 
     const int nT = (Nk + 63) / 64;
-    load_tile_async<ATT_THREADS>(Qs, LD, Qg, d, d, min(64, N - q0), tid);
-    load_tile_async<ATT_THREADS>(Ks, LD, Kg, d, d, min(64, Nk), tid);
-    load_tile_async<ATT_THREADS>(Vs, LD, Vg, d, d, min(64, Nk), tid);
+    load_tile_async<ATT_THREADS>(Qs, LD, Qg, p.q_rs, d, min(64, N - q0), tid);
+    load_tile_async<ATT_THREADS>(Ks, LD, Kg, p.kv_rs, d, min(64, Nk), tid);
+    load_tile_async<ATT_THREADS>(Vs, LD, Vg, p.kv_rs, d, min(64, Nk), tid);
     cp_async_commit();
 
     float o_acc[DPAD / 8][4];
@@ -66,8 +69,8 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_fwd_mma_kernel(const AttnFw
         const int st = jt & 1;
         if (jt + 1 < nT) {
             const int k1 = (jt + 1) * 64;
-            load_tile_async<ATT_THREADS>(Ks + (st ^ 1) * 64 * LD, LD, Kg + (long)k1 * d, d, d, min(64, Nk - k1), tid);
-            load_tile_async<ATT_THREADS>(Vs + (st ^ 1) * 64 * LD, LD, Vg + (long)k1 * d, d, d, min(64, Nk - k1), tid);
+            load_tile_async<ATT_THREADS>(Ks + (st ^ 1) * 64 * LD, LD, Kg + (long)k1 * p.kv_rs, p.kv_rs, d, min(64, Nk - k1), tid);
+            load_tile_async<ATT_THREADS>(Vs + (st ^ 1) * 64 * LD, LD, Vg + (long)k1 * p.kv_rs, p.kv_rs, d, min(64, Nk - k1), tid);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -142,8 +145,9 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_fwd_mma_kernel(const AttnFw
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
     }
-    float* Og = p.o[g] + ((long)h * N + q0) * d;
+    float* Og = p.o[g] ? p.o[g] + ((long)h * N + q0) * d : nullptr;
     float* Lg = p.lse[g] + (long)h * N + q0;
+    unsigned char* Sg = p.os[g] ? reinterpret_cast<unsigned char*>(p.os[g]) + ((long)h * p.os_hs + (long)q0 * p.os_rs) * (p.os_bf16 ? 2 : 4) : nullptr;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         const int row = row0 + (lane >> 2) + r * 8;
@@ -152,7 +156,13 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_fwd_mma_kernel(const AttnFw
 #pragma unroll
         for (int i = 0; i < DPAD / 8; ++i) {
             const int col = i * 8 + (lane & 3) * 2;
-            if (col < d) *reinterpret_cast<float2*>(Og + (long)row * d + col) = make_float2(o_acc[i][2 * r] * inv, o_acc[i][2 * r + 1] * inv);
+            if (col >= d) continue;
+            const float a = o_acc[i][2 * r] * inv, b = o_acc[i][2 * r + 1] * inv;
+            if (Og) *reinterpret_cast<float2*>(Og + (long)row * d + col) = make_float2(a, b);
+            if (Sg) {
+                if (p.os_bf16) *reinterpret_cast<uint32_t*>(Sg + ((long)row * p.os_rs + col) * 2) = pack_bf16(a, b);
+                else *reinterpret_cast<float2*>(Sg + ((long)row * p.os_rs + col) * 4) = make_float2(a, b);
+            }
         }
         if ((lane & 3) == 0) Lg[row] = (m_run[r] + log2f(l_run[r])) * LN2;
     }
@@ -170,9 +180,11 @@ struct AttnBwdParams {
     const bf16* x1; const bf16* x2; const bf16* y1; const bf16* y2;
     const float* lse; const float* delta;   // (H, Nq) natural-log lse, delta
     const float* extra; const float* extra_scale; const int* rowmap; int ex_ld; int M;
-    float* out;                             // (H, n_outer, d) fp32
+    void* out;                              // MODE 0 / unsplit MODE 1: strided (out_rs, out_hs), fp32 or bf16; split MODE 1: fp32 partials
     int H, n_outer, n_inner, d;
     float scale;
+    long x1_rs, x1_hs, x2_rs, x2_hs, y1_rs, y1_hs, y2_rs, y2_hs, out_rs, out_hs;   // element strides (token row, head) per operand
+    int out_bf16;
     int chunk;                              // MODE 1 only: inner (query) tiles per blockIdx.z; out is then (gridDim.z, H, n_outer, d) partial sums
 };
 
@@ -188,10 +200,10 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
     const int h = blockIdx.y, o0 = blockIdx.x * 64;
     const int no = p.n_outer, ni = p.n_inner, d = p.d;
     const int Nq = (MODE == 0) ? no : ni;
-    const bf16* x1g = p.x1 + ((long)h * no + o0) * d;
-    const bf16* x2g = p.x2 + ((long)h * no + o0) * d;
-    const bf16* y1g = p.y1 + (long)h * ni * d;
-    const bf16* y2g = p.y2 + (long)h * ni * d;
+    const bf16* x1g = p.x1 + (long)h * p.x1_hs + (long)o0 * p.x1_rs;
+    const bf16* x2g = p.x2 + (long)h * p.x2_hs + (long)o0 * p.x2_rs;
+    const bf16* y1g = p.y1 + (long)h * p.y1_hs;
+    const bf16* y2g = p.y2 + (long)h * p.y2_hs;
     const float* lse = p.lse + (long)h * Nq;
     const float* delta = p.delta + (long)h * Nq;
 
@@ -202,10 +214,10 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
     const int nT_all = (ni + 63) / 64;
     const int jt0 = (MODE == 1 && p.chunk > 0) ? blockIdx.z * p.chunk : 0;
     const int nT = (MODE == 1 && p.chunk > 0) ? min(nT_all, jt0 + p.chunk) : nT_all;
-    load_tile_async<ATT_THREADS>(X1, LD, x1g, d, d, min(64, no - o0), tid);
-    load_tile_async<ATT_THREADS>(X2, LD, x2g, d, d, min(64, no - o0), tid);
-    load_tile_async<ATT_THREADS>(Y1, LD, y1g + (long)jt0 * 64 * d, d, d, min(64, ni - jt0 * 64), tid);
-    load_tile_async<ATT_THREADS>(Y2, LD, y2g + (long)jt0 * 64 * d, d, d, min(64, ni - jt0 * 64), tid);
+    load_tile_async<ATT_THREADS>(X1, LD, x1g, p.x1_rs, d, min(64, no - o0), tid);
+    load_tile_async<ATT_THREADS>(X2, LD, x2g, p.x2_rs, d, min(64, no - o0), tid);
+    load_tile_async<ATT_THREADS>(Y1, LD, y1g + (long)jt0 * 64 * p.y1_rs, p.y1_rs, d, min(64, ni - jt0 * 64), tid);
+    load_tile_async<ATT_THREADS>(Y2, LD, y2g + (long)jt0 * 64 * p.y2_rs, p.y2_rs, d, min(64, ni - jt0 * 64), tid);
     cp_async_commit();
 
     float acc[DPAD / 8][4];
@@ -230,8 +242,8 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
         const int st = (jt - jt0) & 1;
         if (jt + 1 < nT) {
             const int i1 = (jt + 1) * 64;
-            load_tile_async<ATT_THREADS>(Y1 + (st ^ 1) * 64 * LD, LD, y1g + (long)i1 * d, d, d, min(64, ni - i1), tid);
-            load_tile_async<ATT_THREADS>(Y2 + (st ^ 1) * 64 * LD, LD, y2g + (long)i1 * d, d, d, min(64, ni - i1), tid);
+            load_tile_async<ATT_THREADS>(Y1 + (st ^ 1) * 64 * LD, LD, y1g + (long)i1 * p.y1_rs, p.y1_rs, d, min(64, ni - i1), tid);
+            load_tile_async<ATT_THREADS>(Y2 + (st ^ 1) * 64 * LD, LD, y2g + (long)i1 * p.y2_rs, p.y2_rs, d, min(64, ni - i1), tid);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -293,21 +305,27 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
             }
         __syncthreads();
     }
-    float* og = p.out + ((long)blockIdx.z * p.H + h) * no * d;
+    const bool split = (MODE == 1 && p.chunk > 0);     // partial sums: fp32 (Z, H, n_outer, d) contiguous
+    const long ors = split ? d : p.out_rs;
+    unsigned char* og = reinterpret_cast<unsigned char*>(p.out) +
+                        (split ? ((long)blockIdx.z * p.H + h) * no * d * 4 : (long)h * p.out_hs * (p.out_bf16 ? 2 : 4));
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
         if (orow[r] >= no) continue;
 #pragma unroll
         for (int i = 0; i < DPAD / 8; ++i) {
             const int col = i * 8 + (lane & 3) * 2;
-            if (col < d) *reinterpret_cast<float2*>(og + (long)orow[r] * d + col) = make_float2(acc[i][2 * r] * p.scale, acc[i][2 * r + 1] * p.scale);
+            if (col >= d) continue;
+            const float a = acc[i][2 * r] * p.scale, b = acc[i][2 * r + 1] * p.scale;
+            if (!split && p.out_bf16) *reinterpret_cast<uint32_t*>(og + ((long)orow[r] * ors + col) * 2) = pack_bf16(a, b);
+            else *reinterpret_cast<float2*>(og + ((long)orow[r] * ors + col) * 4) = make_float2(a, b);
         }
     }
 }
 
 // dO (bf16) and delta for the backward:  dO = g_out * coef[row] + g_loss * loss_scale ;
 //   delta[row] = sum_c dO*O  (+ delta_extra[slot(row)]).  One warp per row.
-__global__ void attn_bwd_prep_kernel(const void* __restrict__ g_out, int g_out_bf16, const float* __restrict__ coef,
+__global__ void attn_bwd_prep_kernel(const void* __restrict__ g_out, int g_out_bf16, long g_rs, long g_hs, const float* __restrict__ coef,
                                      const float* __restrict__ g_loss, const float* __restrict__ loss_scale,
                                      const float* __restrict__ o, const float* __restrict__ delta_extra,
                                      const int* __restrict__ rowmap, int M, int H, int N, int d, bf16* __restrict__ d_o,
@@ -321,7 +339,10 @@ __global__ void attn_bwd_prep_kernel(const void* __restrict__ g_out, int g_out_b
     for (int c = lane; c < d; c += 32) {
         const long i = (long)w * d + c;
         float g = 0.f;
-        if (g_out) g = (g_out_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(g_out)[i]) : reinterpret_cast<const float*>(g_out)[i]) * cf;
+        if (g_out) {
+            const long gi = (long)h * g_hs + (long)row * g_rs + c;
+            g = (g_out_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(g_out)[gi]) : reinterpret_cast<const float*>(g_out)[gi]) * cf;
+        }
         if (g_loss) g += g_loss[i] * ls;
         const bf16 gb = __float2bfloat16_rn(g);
         d_o[i] = gb;
@@ -341,7 +362,9 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, bf16* __restrict
 }
 
 // out[i] = sum_z part[z, i] in ascending z (fixed order: deterministic)
-__global__ void sum_partials_kernel(const float* __restrict__ part, int Z, long n, float* __restrict__ out) {
+// (part is (Z, H, rows, d) contiguous; out is strided (row stride rs, head stride hs), fp32 or bf16; d % 4 == 0)
+__global__ void sum_partials_kernel(const float* __restrict__ part, int Z, long n, int rows, int d, void* __restrict__ out, long rs, long hs,
+                                    int out_bf16) {
     const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
     float4 a = *reinterpret_cast<const float4*>(part + i);
@@ -349,7 +372,15 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int Z, long 
         const float4 b = *reinterpret_cast<const float4*>(part + (long)z * n + i);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
     }
-    *reinterpret_cast<float4*>(out + i) = a;
+    const int c = (int)(i % d);
+    const long r = (i / d) % rows, h = i / ((long)d * rows);
+    const long o = h * hs + r * rs + c;
+    if (out_bf16) {
+        uint2 v; v.x = pack_bf16(a.x, a.y); v.y = pack_bf16(a.z, a.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(out) + o) = v;
+    } else {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = a;
+    }
 }
 
 template <int DPAD> static int launch_fwd(const AttnFwdParams& p, cudaStream_t st) {
@@ -387,90 +418,124 @@ int attn_fwd_mma(const AttnFwdParams& p, cudaStream_t st) {
     return set_error(GD_ERR_UNSUPPORTED, "head_dim %d > 160", p.d);
 }
 
+template <int MODE> static int bwd_dispatch(const AttnBwdParams& p, int d, cudaStream_t st, int Z) {
+    if (d <= 48) return launch_bwd<48, MODE>(p, st, Z);
+    if (d <= 80) return launch_bwd<80, MODE>(p, st, Z);
+    if (d <= 160) return launch_bwd<160, MODE>(p, st, Z);
+    return set_error(GD_ERR_UNSUPPORTED, "head_dim %d > 160", d);
+}
+
 }  // namespace gd
 
 using namespace gd;
 
 extern "C" {
 
-// Forward over G query streams, each (H, N, d) bf16 against its own K/V (H, Nk, d) bf16; o[g] (H,N,d) fp32, lse[g] (H,N).
-// Pointer arrays are HOST arrays of device pointers.
-int gd_attn_fwd_generic(const void* const* q, const void* const* k, const void* const* v, void* const* o, void* const* lse, int G,
-                        int H, int N, int Nk, int d, float scale, void* stream) {
-    GD_CHECK_ARG(q && k && v && o && lse && G > 0 && G <= ATT_MAXG && H > 0 && N > 0 && Nk > 0 && d > 0 && (d % 8) == 0);
+// Strides.  Every q / k / v / output operand below is one (H, N, d) "slab" addressed as base + h * head_stride + n * row_stride + c
+// (element strides).  `strides` is a HOST array of 6 longs {q_row, q_head, kv_row, kv_head, os_row, os_head}; NULL means contiguous
+// (H, N, d) slabs (row = d, head = N * d) -- the reference's head_to_batch_dim layout (attention_sharing.py:210-242).  The projection
+// layout (B, N, H*d) that to_q / to_k / to_v produce is {H*d, d}: the kernels read it in place, no head permute copy.
+static void fill_strides(const long* s, int N, int Nk, int d, long* q_rs, long* q_hs, long* kv_rs, long* kv_hs, long* o_rs, long* o_hs) {
+    *q_rs = s ? s[0] : d; *q_hs = s ? s[1] : (long)N * d;
+    *kv_rs = s ? s[2] : d; *kv_hs = s ? s[3] : (long)Nk * d;
+    *o_rs = s ? s[4] : d; *o_hs = s ? s[5] : (long)N * d;
+}
+static bool strides_ok(const long* s) {
+    if (!s) return true;
+    for (int i = 0; i < 6; ++i) if (s[i] <= 0 || (s[i] % 8) != 0) return false;   // 16-byte rows for cp.async / TMA
+    return true;
+}
+
+// Forward over G query streams, each an (H, N, d) bf16 slab against its own K/V (H, Nk, d) slabs.  Per stream: o[g] (H,N,d) fp32 contiguous
+// and / or os[g] strided in the layout of q (bf16 if os_is_bf16 else fp32) -- at least one of the two; lse[g] (H,N) fp32.
+// Pointer arrays are HOST arrays of device pointers; os_host may be NULL (no strided outputs).
+int gd_attn_fwd_generic(const void* const* q, const void* const* k, const void* const* v, void* const* o, void* const* lse, void* const* os,
+                        int G, int H, int N, int Nk, int d, float scale, const long* strides, int os_is_bf16, void* stream) {
+    GD_CHECK_ARG(q && k && v && o && lse && G > 0 && G <= ATT_MAXG && H > 0 && N > 0 && Nk > 0 && d > 0 && (d % 8) == 0 && strides_ok(strides));
     AttnFwdParams p;
     for (int g = 0; g < G; ++g) {
-        GD_CHECK_ARG(q[g] && k[g] && v[g] && o[g] && lse[g]);
+        GD_CHECK_ARG(q[g] && k[g] && v[g] && lse[g] && (o[g] || (os && os[g])));
         p.q[g] = (const bf16*)q[g]; p.k[g] = (const bf16*)k[g]; p.v[g] = (const bf16*)v[g];
-        p.o[g] = (float*)o[g]; p.lse[g] = (float*)lse[g];
+        p.o[g] = (float*)o[g]; p.lse[g] = (float*)lse[g]; p.os[g] = os ? os[g] : nullptr;
     }
-    p.G = G; p.H = H; p.N = N; p.Nk = Nk; p.d = d; p.scale = scale;
+    p.G = G; p.H = H; p.N = N; p.Nk = Nk; p.d = d; p.scale = scale; p.os_bf16 = os_is_bf16;
+    fill_strides(strides, N, Nk, d, &p.q_rs, &p.q_hs, &p.kv_rs, &p.kv_hs, &p.os_rs, &p.os_hs);
     return attn_fwd_mma(p, (cudaStream_t)stream);
 }
 
-// dO / delta preparation (see attn_bwd_prep_kernel)
-int gd_attn_bwd_prep(const void* g_out, int g_out_is_bf16, const float* coef, const float* g_loss, const float* loss_scale,
+// dO / delta preparation (see attn_bwd_prep_kernel).  g_out is strided (g_strides = {row, head}, NULL = contiguous (H,N,d)).
+int gd_attn_bwd_prep(const void* g_out, int g_out_is_bf16, const long* g_strides, const float* coef, const float* g_loss, const float* loss_scale,
                      const float* o, const float* delta_extra, const int* rowmap, int M, int H, int N, int d, void* d_o_bf16,
                      float* delta, void* stream) {
     GD_CHECK_ARG(o && d_o_bf16 && delta && (g_out || g_loss) && H > 0 && N > 0 && d > 0);
     const long warps = (long)H * N;
-    attn_bwd_prep_kernel<<<ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(g_out, g_out_is_bf16, coef, g_loss, loss_scale, o,
+    const long g_rs = g_strides ? g_strides[0] : d, g_hs = g_strides ? g_strides[1] : (long)N * d;
+    attn_bwd_prep_kernel<<<ceil_div(warps * 32, 256), 256, 0, (cudaStream_t)stream>>>(g_out, g_out_is_bf16, g_rs, g_hs, coef, g_loss, loss_scale, o,
                                                                                      delta_extra, rowmap, M, H, N, d, (bf16*)d_o_bf16, delta);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }
 
-// mode 0: dQ (H,N,d) ; mode 1: dK (H,Nk,d).  q, d_o (H,N,d) bf16; k, v (H,Nk,d) bf16; lse, delta (H,N) fp32.
+static int bwd_fill(AttnBwdParams& p, int mode, const void* q, const void* k, const void* v, const void* d_o, int N, int Nk, int d,
+                    const long* strides) {
+    long q_rs, q_hs, kv_rs, kv_hs, o_rs, o_hs;
+    fill_strides(strides, N, Nk, d, &q_rs, &q_hs, &kv_rs, &kv_hs, &o_rs, &o_hs);
+    if (!strides && mode == 1) o_hs = (long)Nk * d;
+    p.out_rs = o_rs; p.out_hs = o_hs;
+    if (mode == 0) {
+        p.x1 = (const bf16*)q; p.x1_rs = q_rs; p.x1_hs = q_hs;
+        p.x2 = (const bf16*)d_o; p.x2_rs = d; p.x2_hs = (long)N * d;
+        p.y1 = (const bf16*)k; p.y1_rs = kv_rs; p.y1_hs = kv_hs;
+        p.y2 = (const bf16*)v; p.y2_rs = kv_rs; p.y2_hs = kv_hs;
+        p.n_outer = N; p.n_inner = Nk;
+    } else {
+        p.x1 = (const bf16*)k; p.x1_rs = kv_rs; p.x1_hs = kv_hs;
+        p.x2 = (const bf16*)v; p.x2_rs = kv_rs; p.x2_hs = kv_hs;
+        p.y1 = (const bf16*)q; p.y1_rs = q_rs; p.y1_hs = q_hs;
+        p.y2 = (const bf16*)d_o; p.y2_rs = d; p.y2_hs = (long)N * d;
+        p.n_outer = Nk; p.n_inner = N;
+    }
+    return GD_OK;
+}
+
+// mode 0: out = dQ, strided like q; mode 1: out = dK, strided like k.  q (H,N,d), k, v (H,Nk,d) bf16 slabs (strides as above; entries 4,5 =
+// row / head stride of `out`); d_o (H,N,d) bf16 contiguous; lse, delta (H,N) fp32; out fp32 or bf16 (out_is_bf16).
 int gd_attn_bwd(int mode, const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
-                const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* out, int H, int N, int Nk,
-                int d, float scale, void* stream) {
-    GD_CHECK_ARG(q && k && v && d_o && lse && delta && out && H > 0 && N > 0 && Nk > 0 && d > 0 && (d % 8) == 0);
+                const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* out, int H, int N, int Nk,
+                int d, float scale, const long* strides, int out_is_bf16, void* stream) {
+    GD_CHECK_ARG(q && k && v && d_o && lse && delta && out && H > 0 && N > 0 && Nk > 0 && d > 0 && (d % 8) == 0 && strides_ok(strides));
     GD_CHECK_ARG(mode == 0 || mode == 1);
     GD_CHECK_ARG((extra == nullptr) == (rowmap == nullptr));
     AttnBwdParams p;
     p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.out = out;
-    p.H = H; p.d = d; p.scale = scale; p.chunk = 0;
+    p.H = H; p.d = d; p.scale = scale; p.chunk = 0; p.out_bf16 = out_is_bf16;
+    bwd_fill(p, mode, q, k, v, d_o, N, Nk, d, strides);
     cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 0) {
-        p.x1 = (const bf16*)q; p.x2 = (const bf16*)d_o; p.y1 = (const bf16*)k; p.y2 = (const bf16*)v; p.n_outer = N; p.n_inner = Nk;
-        if (d <= 48) return launch_bwd<48, 0>(p, st);
-        if (d <= 80) return launch_bwd<80, 0>(p, st);
-        if (d <= 160) return launch_bwd<160, 0>(p, st);
-    } else {
-        p.x1 = (const bf16*)k; p.x2 = (const bf16*)v; p.y1 = (const bf16*)q; p.y2 = (const bf16*)d_o; p.n_outer = Nk; p.n_inner = N;
-        if (d <= 48) return launch_bwd<48, 1>(p, st);
-        if (d <= 80) return launch_bwd<80, 1>(p, st);
-        if (d <= 160) return launch_bwd<160, 1>(p, st);
-    }
-    return set_error(GD_ERR_UNSUPPORTED, "head_dim %d > 160", d);
+    return mode == 0 ? bwd_dispatch<0>(p, d, st, 1) : bwd_dispatch<1>(p, d, st, 1);
 }
 
-// dK as gd_attn_bwd mode 1, with the query range split over the grid: workspace (>= splits * H * Nk * d floats, H*Nk*d % 4 == 0) receives
+// dK as gd_attn_bwd mode 1, with the query range split over the grid: workspace (>= splits * H * Nk * d floats, d % 4 == 0) receives
 // the per-split partial sums, which are then added in ascending order (deterministic).  splits <= 1 or no workspace: same as mode 1.
 int gd_attn_bwd_dk_split(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
-                         const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* dk, float* workspace,
-                         int splits, int H, int N, int Nk, int d, float scale, void* stream) {
+                         const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* dk, float* workspace,
+                         int splits, int H, int N, int Nk, int d, float scale, const long* strides, int out_is_bf16, void* stream) {
     const int nT = (N + 63) / 64;
     if (splits > nT) splits = nT;
-    if (!workspace || splits <= 1 || ((long)H * Nk * d) % 4 != 0)
-        return gd_attn_bwd(1, q, k, v, d_o, lse, delta, extra, extra_scale, rowmap, ex_ld, M, dk, H, N, Nk, d, scale, stream);
-    GD_CHECK_ARG(q && k && v && d_o && lse && delta && dk && H > 0 && N > 0 && Nk > 0 && d > 0 && (d % 8) == 0);
+    if (!workspace || splits <= 1)
+        return gd_attn_bwd(1, q, k, v, d_o, lse, delta, extra, extra_scale, rowmap, ex_ld, M, dk, H, N, Nk, d, scale, strides, out_is_bf16, stream);
+    GD_CHECK_ARG(q && k && v && d_o && lse && delta && dk && H > 0 && N > 0 && Nk > 0 && d > 0 && (d % 8) == 0 && strides_ok(strides));
     GD_CHECK_ARG((extra == nullptr) == (rowmap == nullptr));
     AttnBwdParams p;
     p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.out = workspace;
-    p.H = H; p.d = d; p.scale = scale;
+    p.H = H; p.d = d; p.scale = scale; p.out_bf16 = 0;
     p.chunk = (nT + splits - 1) / splits;
     const int Z = (nT + p.chunk - 1) / p.chunk;
-    p.x1 = (const bf16*)k; p.x2 = (const bf16*)v; p.y1 = (const bf16*)q; p.y2 = (const bf16*)d_o; p.n_outer = Nk; p.n_inner = N;
+    bwd_fill(p, 1, q, k, v, d_o, N, Nk, d, strides);
     cudaStream_t st = (cudaStream_t)stream;
-    int rc;
-    if (d <= 48) rc = launch_bwd<48, 1>(p, st, Z);
-    else if (d <= 80) rc = launch_bwd<80, 1>(p, st, Z);
-    else if (d <= 160) rc = launch_bwd<160, 1>(p, st, Z);
-    else return set_error(GD_ERR_UNSUPPORTED, "head_dim %d > 160", d);
+    int rc = bwd_dispatch<1>(p, d, st, Z);
     if (rc != GD_OK) return rc;
     const long n = (long)H * Nk * d;
-    sum_partials_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(workspace, Z, n, dk);
+    sum_partials_kernel<<<ceil_div(n / 4, 256), 256, 0, st>>>(workspace, Z, n, Nk, d, dk, p.out_rs, p.out_hs, out_is_bf16);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }

@@ -32,8 +32,11 @@ struct Sm100Maps {
     CUtensorMap v[SM100_MAXG];
 };
 struct Sm100Params {
-    float* o[SM100_MAXG];
+    float* o[SM100_MAXG];      // (H, N, d) fp32 contiguous, or NULL
     float* lse[SM100_MAXG];
+    void* os[SM100_MAXG];      // strided output (row stride os_rs, head stride os_hs, elements; bf16 or fp32), or NULL
+    long os_rs, os_hs;
+    int os_bf16;
     int H, N, d;
     float scale2;  // scale * log2(e)
 };
@@ -72,6 +75,11 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1) : "memory");
+}
+// operands are 3-D tensors (d, N, H) with arbitrary row / head strides: coordinates (column, token row, head)
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -205,7 +213,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
     const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
     const int N = p.N;
     const int nT = N / BN;
-    const int row_base = h * N;     // row offset of this head inside the (H*N, d) view
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
@@ -228,18 +235,18 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
         if (lane == 0) {
             mbar_expect_tx(q_full, OP_BYTES);
 #pragma unroll
-            for (int b = 0; b < KB; ++b) tma_load_2d(sQ + b * TILE_BYTES, &maps.q[g], q_full, b * 64, row_base + q0);
+            for (int b = 0; b < KB; ++b) tma_load_3d(sQ + b * TILE_BYTES, &maps.q[g], q_full, b * 64, q0, h);
             for (int j = 0; j < nT; ++j) {
                 const int s = j & 1;
                 const uint32_t ph = (j >> 1) & 1;
                 mbar_wait_relaxed(k_empty + s, ph ^ 1);
                 mbar_expect_tx(k_full + s, OP_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_2d(sK + s * OP_BYTES + b * TILE_BYTES, &maps.k[g], k_full + s, b * 64, row_base + j * BN);
+                for (int b = 0; b < KB; ++b) tma_load_3d(sK + s * OP_BYTES + b * TILE_BYTES, &maps.k[g], k_full + s, b * 64, j * BN, h);
                 mbar_wait_relaxed(v_empty + s, ph ^ 1);
                 mbar_expect_tx(v_full + s, OP_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_2d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v[g], v_full + s, b * 64, row_base + j * BN);
+                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v[g], v_full + s, b * 64, j * BN, h);
             }
         }
     } else if (warp == 5) {
@@ -355,17 +362,38 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
         tc_fence_after();
         const int row = q0 + warp * 32 + lane;
         const float inv = 1.0f / l_run;
-        float* og = p.o[g] + ((long)h * N + row) * D;
+        float* og = p.o[g] ? p.o[g] + ((long)h * N + row) * D : nullptr;
+        unsigned char* sg = p.os[g] ? reinterpret_cast<unsigned char*>(p.os[g]) + ((long)h * p.os_hs + (long)row * p.os_rs) * (p.os_bf16 ? 2 : 4) : nullptr;
 #pragma unroll
         for (int c = 0; c < DV / 16; ++c) {
             uint32_t orr[16];
             tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
             tmem_wait_ld();
+            float f[16];
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-                if (c * 16 + e < D)
-                    *reinterpret_cast<float4*>(og + c * 16 + e) = make_float4(__uint_as_float(orr[e]) * inv, __uint_as_float(orr[e + 1]) * inv,
-                                                                             __uint_as_float(orr[e + 2]) * inv, __uint_as_float(orr[e + 3]) * inv);
+            for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(orr[e]) * inv;
+            if (og) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    if (c * 16 + e < D) *reinterpret_cast<float4*>(og + c * 16 + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+            }
+            if (sg) {
+                if (p.os_bf16) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 8)
+                        if (c * 16 + e < D) {
+                            uint4 v;
+                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[e], f[e + 1]), b1 = __floats2bfloat162_rn(f[e + 2], f[e + 3]);
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[e + 4], f[e + 5]), b3 = __floats2bfloat162_rn(f[e + 6], f[e + 7]);
+                            v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
+                            v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
+                            *reinterpret_cast<uint4*>(sg + (c * 16 + e) * 2) = v;
+                        }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4)
+                        if (c * 16 + e < D) *reinterpret_cast<float4*>(sg + (c * 16 + e) * 4) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+                }
             }
         }
         p.lse[g][(long)h * N + row] = (m_run + log2f(l_run)) * 0.6931471805599453f;
@@ -396,7 +424,9 @@ struct Sm100BwdMaps { CUtensorMap q, k, v, d_o; };
 struct Sm100BwdParams {
     const float* lse; const float* delta;
     const float* extra; const float* extra_scale; const int* rowmap; int ex_ld, M;
-    float* dq;
+    void* dq;                  // strided (dq_rs, dq_hs elements), fp32 or bf16
+    long dq_rs, dq_hs;
+    int dq_bf16;
     int H, N;
     float scale, scale2;
 };
@@ -438,7 +468,6 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
     const int h = blockIdx.y, q0 = blockIdx.x * BM;
     const int N = p.N;
     const int nT = N / BN;
-    const int row_base = h * N;
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
@@ -463,8 +492,8 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
             mbar_expect_tx(q_full, 2 * OP_BYTES);
 #pragma unroll
             for (int b = 0; b < KB; ++b) {
-                tma_load_2d(sQ + b * TILE_BYTES, &maps.q, q_full, b * 64, row_base + q0);
-                tma_load_2d(sDO + b * TILE_BYTES, &maps.d_o, q_full, b * 64, row_base + q0);
+                tma_load_3d(sQ + b * TILE_BYTES, &maps.q, q_full, b * 64, q0, h);
+                tma_load_3d(sDO + b * TILE_BYTES, &maps.d_o, q_full, b * 64, q0, h);
             }
             for (int j = 0; j < nT; ++j) {
                 const int s = j & 1;
@@ -474,11 +503,11 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
                 mbar_wait_relaxed(k_empty + ks, kph ^ 1);
                 mbar_expect_tx(k_full + ks, OP_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_2d(sK + ks * OP_BYTES + b * TILE_BYTES, &maps.k, k_full + ks, b * 64, row_base + j * BN);
+                for (int b = 0; b < KB; ++b) tma_load_3d(sK + ks * OP_BYTES + b * TILE_BYTES, &maps.k, k_full + ks, b * 64, j * BN, h);
                 mbar_wait_relaxed(v_empty + s, ph ^ 1);
                 mbar_expect_tx(v_full + s, OP_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_2d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v, v_full + s, b * 64, row_base + j * BN);
+                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v, v_full + s, b * 64, j * BN, h);
             }
         }
     } else if (warp == NEW + 1) {
@@ -587,7 +616,7 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
         // epilogue: dQ * scale -> global fp32; the two warps of a quarter split the 16-column chunks
         mbar_wait(dq_done, (nT - 1) & 1);
         tc_fence_after();
-        float* og = p.dq + ((long)h * N + row) * D;
+        unsigned char* og = reinterpret_cast<unsigned char*>(p.dq) + ((long)h * p.dq_hs + (long)row * p.dq_rs) * (p.dq_bf16 ? 2 : 4);
         const float sc = p.scale;
 #pragma unroll
         for (int c = 0; c < DV / 16; ++c) {
@@ -595,11 +624,24 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
             uint32_t orr[16];
             tmem_ld16(tmem + lane_off + COL_DQ + c * 16, orr);
             tmem_wait_ld();
+            float f[16];
 #pragma unroll
-            for (int e = 0; e < 16; e += 4) {
-                if (c * 16 + e < D)
-                    *reinterpret_cast<float4*>(og + c * 16 + e) = make_float4(__uint_as_float(orr[e]) * sc, __uint_as_float(orr[e + 1]) * sc,
-                                                                             __uint_as_float(orr[e + 2]) * sc, __uint_as_float(orr[e + 3]) * sc);
+            for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(orr[e]) * sc;
+            if (p.dq_bf16) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 8)
+                    if (c * 16 + e < D) {
+                        uint4 v;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[e], f[e + 1]), b1 = __floats2bfloat162_rn(f[e + 2], f[e + 3]);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[e + 4], f[e + 5]), b3 = __floats2bfloat162_rn(f[e + 6], f[e + 7]);
+                        v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
+                        v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
+                        *reinterpret_cast<uint4*>(og + (c * 16 + e) * 2) = v;
+                    }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    if (c * 16 + e < D) *reinterpret_cast<float4*>(og + (c * 16 + e) * 4) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
             }
         }
     }
@@ -627,15 +669,18 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// (rows, d) bf16 row-major viewed as a 2-D tensor; box = 64 columns (128 B, zero-filled past d) x 128 rows, SWIZZLE_128B
-static int make_map(CUtensorMap* m, const void* base, long rows, int d, int box_rows) {
+// one (H, N, d) bf16 slab as a 3-D tensor (d, N, H) with element strides (1, rs, hs); box = 64 columns (128 B, zero-filled past d) x
+// box_rows tokens x 1 head, SWIZZLE_128B.  Contiguous slabs: rs = d, hs = N*d; projection layout (N, H*d): rs = H*d, hs = d.
+static int make_map(CUtensorMap* m, const void* base, int N, int H, int d, long rs, long hs, int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)d * sizeof(bf16)};
-    cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if ((rs % 8) != 0 || (hs % 8) != 0 || (reinterpret_cast<uintptr_t>(base) & 15) != 0)
+        return set_error(GD_ERR_INVALID, "attention operand: base and strides must be 16-byte aligned (rs=%ld hs=%ld)", rs, hs);
+    cuuint64_t gdim[3] = {(cuuint64_t)d, (cuuint64_t)N, (cuuint64_t)H};
+    cuuint64_t gstr[2] = {(cuuint64_t)rs * sizeof(bf16), (cuuint64_t)hs * sizeof(bf16)};
+    cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(GD_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return GD_OK;
@@ -690,22 +735,28 @@ template <int D, int POLY> static int launch_bwd_sm100(const Sm100BwdMaps& maps,
 
 using namespace gd;
 
-extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, const void* const* v, void* const* o, void* const* lse, int G, int H,
-                                 int N, int Nk, int d, float scale, void* stream) {
+extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, const void* const* v, void* const* o, void* const* lse,
+                                 void* const* os, int G, int H, int N, int Nk, int d, float scale, const long* strides, int os_is_bf16,
+                                 void* stream) {
     GD_CHECK_ARG(q && k && v && o && lse && G > 0 && G <= SM100_MAXG && H > 0);
     if (!(N == Nk && N % 128 == 0 && (d == 40 || d == 80)))
         return set_error(GD_ERR_UNSUPPORTED, "gd_attn_fwd_sm100 serves N == Nk, N %% 128 == 0, d in {40, 80}; got N=%d Nk=%d d=%d", N, Nk, d);
+    const long q_rs = strides ? strides[0] : d, q_hs = strides ? strides[1] : (long)N * d;
+    const long kv_rs = strides ? strides[2] : d, kv_hs = strides ? strides[3] : (long)N * d;
     Sm100Maps maps;
     Sm100Params p;
     for (int g = 0; g < G; ++g) {
-        GD_CHECK_ARG(q[g] && k[g] && v[g] && o[g] && lse[g]);
+        GD_CHECK_ARG(q[g] && k[g] && v[g] && lse[g] && (o[g] || (os && os[g])));
         int rc;
-        if ((rc = make_map(&maps.q[g], q[g], (long)H * N, d, BM)) != GD_OK) return rc;
-        if ((rc = make_map(&maps.k[g], k[g], (long)H * N, d, BN)) != GD_OK) return rc;
-        if ((rc = make_map(&maps.v[g], v[g], (long)H * N, d, BN)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.q[g], q[g], N, H, d, q_rs, q_hs, BM)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.k[g], k[g], N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.v[g], v[g], N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
         p.o[g] = (float*)o[g];
         p.lse[g] = (float*)lse[g];
+        p.os[g] = os ? os[g] : nullptr;
     }
+    p.os_rs = strides ? strides[4] : d; p.os_hs = strides ? strides[5] : (long)N * d; p.os_bf16 = os_is_bf16;
+    if (os && ((p.os_rs % 8) != 0 || (p.os_hs % 8) != 0)) return set_error(GD_ERR_INVALID, "gd_attn_fwd_sm100: output strides must be multiples of 8");
     p.H = H; p.N = N; p.d = d; p.scale2 = scale * 1.4426950408889634f;
     if (d == 40) return dispatch_sm100<40>(maps, p, G, (cudaStream_t)stream);
     return dispatch_sm100<80>(maps, p, G, (cudaStream_t)stream);
@@ -722,21 +773,25 @@ extern "C" int gd_attn_sm100_config(int poly) {
 
 // dQ of softmax(scale q k^T) v for the self-attention levels (N == Nk, N % 128 == 0, d in {40, 80}); same operands as gd_attn_bwd mode 0.
 extern "C" int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
-                                 const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* dq, int H, int N,
-                                 int d, float scale, void* stream) {
+                                 const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* dq, int H, int N,
+                                 int d, float scale, const long* strides, int dq_is_bf16, void* stream) {
     GD_CHECK_ARG(q && k && v && d_o && lse && delta && dq && H > 0);
     GD_CHECK_ARG((extra == nullptr) == (rowmap == nullptr));
     if (!(N % 128 == 0 && (d == 40 || d == 80)))
         return set_error(GD_ERR_UNSUPPORTED, "gd_attn_bwd_sm100 serves N %% 128 == 0, d in {40, 80}; got N=%d d=%d", N, d);
     if (extra && (ex_ld % 4 != 0 || ex_ld < N)) return set_error(GD_ERR_INVALID, "gd_attn_bwd_sm100: extra row stride %d must be >= N and a multiple of 4", ex_ld);
+    const long q_rs = strides ? strides[0] : d, q_hs = strides ? strides[1] : (long)N * d;
+    const long kv_rs = strides ? strides[2] : d, kv_hs = strides ? strides[3] : (long)N * d;
     Sm100BwdMaps maps;
     int rc;
-    if ((rc = make_map(&maps.q, q, (long)H * N, d, BM)) != GD_OK) return rc;
-    if ((rc = make_map(&maps.d_o, d_o, (long)H * N, d, BM)) != GD_OK) return rc;
-    if ((rc = make_map(&maps.k, k, (long)H * N, d, BN)) != GD_OK) return rc;
-    if ((rc = make_map(&maps.v, v, (long)H * N, d, BN)) != GD_OK) return rc;
+    if ((rc = make_map(&maps.q, q, N, H, d, q_rs, q_hs, BM)) != GD_OK) return rc;
+    if ((rc = make_map(&maps.d_o, d_o, N, H, d, d, (long)N * d, BM)) != GD_OK) return rc;
+    if ((rc = make_map(&maps.k, k, N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
+    if ((rc = make_map(&maps.v, v, N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
     Sm100BwdParams p;
     p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.dq = dq;
+    p.dq_rs = strides ? strides[4] : d; p.dq_hs = strides ? strides[5] : (long)N * d; p.dq_bf16 = dq_is_bf16;
+    if ((p.dq_rs % 8) != 0 || (p.dq_hs % 8) != 0) return set_error(GD_ERR_INVALID, "gd_attn_bwd_sm100: dq strides must be multiples of 8");
     p.H = H; p.N = N; p.scale = scale; p.scale2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
     // all exponentials on the MUFU: with ~4.5 instructions per score the elementwise warps are issue-bound, the polynomial only adds to that

@@ -131,12 +131,16 @@ using namespace gd;
 extern "C" {
 
 // P[h, m, :] = softmax row of q[h, rows[m] (or m), :] against k[h] given its natural-log lse; bf16 out, row stride ldp
-// (multiple of 8, >= Nk; columns Nk..ldp zero-filled).  q (H,N,d), k (H,Nk,d) bf16; lse (H,N).
+// (multiple of 8, >= Nk; columns Nk..ldp zero-filled).  q (H,N,d), k (H,Nk,d) bf16 slabs; qk_strides = {q_row, q_head, k_row, k_head}
+// element strides (HOST array; NULL = contiguous); lse (H,N).
 int gd_attn_probs(const void* q, const void* k, const float* lse, const int* rows, int M, int H, int N, int Nk, int d, float scale,
-                  void* p_out, int ldp, void* stream) {
+                  void* p_out, int ldp, const long* qk_strides, void* stream) {
     GD_CHECK_ARG(q && k && lse && p_out && H > 0 && N > 0 && Nk > 0 && M > 0 && d > 0 && (d % 8) == 0 && (ldp % 8) == 0 && ldp >= Nk);
     GemmParams p = {};
-    p.a = (const bf16*)q; p.b = (const bf16*)k; p.a_hs = (long)N * d; p.b_hs = (long)Nk * d; p.lda = d; p.ldb = d; p.a_rows = rows;
+    p.a = (const bf16*)q; p.b = (const bf16*)k; p.a_rows = rows;
+    p.lda = qk_strides ? (int)qk_strides[0] : d; p.a_hs = qk_strides ? qk_strides[1] : (long)N * d;
+    p.ldb = qk_strides ? (int)qk_strides[2] : d; p.b_hs = qk_strides ? qk_strides[3] : (long)Nk * d;
+    GD_CHECK_ARG((p.lda % 8) == 0 && (p.ldb % 8) == 0 && (p.a_hs % 8) == 0 && (p.b_hs % 8) == 0);
     p.H = H; p.M = M; p.N = Nk; p.K = d; p.lse = lse; p.lse_hs = N; p.scale = scale; p.p_out = (bf16*)p_out; p.p_hs = (long)M * ldp; p.ldp = ldp;
     dim3 grid(ceil_div(ldp, GE_BN), ceil_div(M, GE_BM), H);
     gemm_nt_kernel<0><<<grid, GE_THREADS, 0, (cudaStream_t)stream>>>(p);

@@ -513,6 +513,29 @@ int gd_splat_composite(const void* src, int src_dtype, int layout, const int* id
     return GD_OK;
 }
 
+// The per-layer query warp on one (B = heads, P, C = head_dim) slab with explicit element strides: src / out addressed as
+// base + b * head_stride + p * row_stride + c (src_strides / out_strides = {row, head}, HOST arrays; NULL = contiguous (B, P, C)).  One index
+// (P, K) shared by all heads.  Same arithmetic as gd_splat_composite (layout 1), bit for bit.
+int gd_splat_composite_rows(const void* src, int src_dtype, const long* src_strides, const int* idx, const float* dist2, int B, int P, int C,
+                            int K, float r2, float tau, const float* blend_mask, int post, void* out, int out_dtype, const long* out_strides,
+                            void* stream) {
+    GD_CHECK_ARG(src && idx && dist2 && out && B > 0 && P > 0 && C > 0 && K > 0 && K <= 32);
+    GD_CHECK_ARG((src_dtype == 0 || src_dtype == 1) && (out_dtype == 0 || out_dtype == 1));
+    const long sp = src_strides ? src_strides[0] : C, sb = src_strides ? src_strides[1] : (long)P * C;
+    const long op = out_strides ? out_strides[0] : C, ob = out_strides ? out_strides[1] : (long)P * C;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int gr = ceil_div((long)P * 32, 256);
+#define GD_LAUNCH_ROWS(TI, TO) \
+    splat_composite_rows_kernel<TI, TO><<<gr, 256, 0, st>>>((const TI*)src, sb, sp, idx, dist2, B, P, C, K, r2, tau, blend_mask, post, (TO*)out, ob, op)
+    if (src_dtype == 0 && out_dtype == 0) GD_LAUNCH_ROWS(float, float);
+    else if (src_dtype == 0 && out_dtype == 1) GD_LAUNCH_ROWS(float, __nv_bfloat16);
+    else if (src_dtype == 1 && out_dtype == 0) GD_LAUNCH_ROWS(__nv_bfloat16, float);
+    else GD_LAUNCH_ROWS(__nv_bfloat16, __nv_bfloat16);
+#undef GD_LAUNCH_ROWS
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
 int gd_mesh_mask(const float* coords, const float* mask, int H, int W, float blur, float* out, void* stream) {
     GD_CHECK_ARG(coords && mask && out && H == W && H > 1);
     cudaStream_t st = (cudaStream_t)stream;

@@ -199,14 +199,17 @@ __global__ void smooth5_kernel(const float* __restrict__ u, Gauss5 gk, int H, in
 // out[h,p,c] = a[h,p,c] * ma[p] + b[h,p,c] * mb[p]   (attention_processors.py:617-624, 922-925)
 template <typename TOut>
 __global__ void blend_rows_kernel(const float* __restrict__ a, const float* __restrict__ ma, const float* __restrict__ b,
-                                  const float* __restrict__ mb, int N, int d, long total, TOut* __restrict__ out) {
+                                  const float* __restrict__ mb, int N, int d, long total, TOut* __restrict__ out, long o_rs, long o_hs) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
+    const int c = (int)(i % d);
     const int p = (int)((i / d) % N);
+    const long h = i / ((long)d * N);
     float v = b[i] * (mb ? mb[p] : 1.0f);
     if (a) v = a[i] * ma[p] + v;
-    if (sizeof(TOut) == 2) reinterpret_cast<__nv_bfloat16*>(out)[i] = __float2bfloat16_rn(v);
-    else reinterpret_cast<float*>(out)[i] = v;
+    const long o = h * o_hs + (long)p * o_rs + c;
+    if (sizeof(TOut) == 2) reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(out)[o] = v;
 }
 
 }  // namespace gd
@@ -273,11 +276,12 @@ int gd_amodal_target(const float* e, const float* m_edit, const int* idx4, const
 }
 
 int gd_blend_rows(const float* a, const float* ma, const float* b, const float* mb, int H, int N, int d, void* out, int out_is_bf16,
-                  void* stream) {
+                  const long* out_strides, void* stream) {
     GD_CHECK_ARG(b && out && H > 0 && N > 0 && d > 0 && (a == nullptr || ma != nullptr));
     const long total = (long)H * N * d;
-    if (out_is_bf16) blend_rows_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(a, ma, b, mb, N, d, total, (__nv_bfloat16*)out);
-    else blend_rows_kernel<float><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(a, ma, b, mb, N, d, total, (float*)out);
+    const long o_rs = out_strides ? out_strides[0] : d, o_hs = out_strides ? out_strides[1] : (long)N * d;
+    if (out_is_bf16) blend_rows_kernel<__nv_bfloat16><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(a, ma, b, mb, N, d, total, (__nv_bfloat16*)out, o_rs, o_hs);
+    else blend_rows_kernel<float><<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(a, ma, b, mb, N, d, total, (float*)out, o_rs, o_hs);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }

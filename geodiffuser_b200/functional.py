@@ -90,31 +90,102 @@ def _bf16(t):
     return t.detach().to(torch.bfloat16).contiguous()
 
 
-def attention_forward(qs, ks, vs, scale):
-    """G query streams (H,N,d) bf16 against K/V (H,Nk,d) bf16 -> O (G,H,N,d) fp32, LSE (G,H,N) fp32."""
+class ProjView:
+    """q / k / v exactly as the to_q / to_k / to_v projections produce them -- one contiguous (B, N, H*d) tensor -- presented with the
+    (B*H, N, d) shape the reference's controllers receive (attention_sharing.py:127-144).  The kernels address each (H, N, d) slab of it in
+    place (row stride H*d, head stride d), so the head_to_batch_dim / batch_to_head_dim permute copies of the reference (4 per attention
+    layer, 128 per UNet evaluation) do not exist on this path.  A controller that is handed ProjViews returns the attention output in the
+    same projection layout, (B, N, H*d), ready for to_out."""
+    __slots__ = ("t", "heads")
+
+    def __init__(self, t, heads):
+        assert t.dim() == 3 and t.shape[2] % heads == 0
+        self.t = t if t.is_contiguous() else t.contiguous()
+        self.heads = heads
+
+    @property
+    def shape(self):
+        b, n, c = self.t.shape
+        return torch.Size((b * self.heads, n, c // self.heads))
+
+    device = property(lambda self: self.t.device)
+    is_cuda = property(lambda self: self.t.is_cuda)
+    dtype = property(lambda self: self.t.dtype)
+    requires_grad = property(lambda self: self.t.requires_grad)
+
+
+class _Layout:
+    """element strides of the (H, N, d) slabs of q, k / v and of the outputs, for the two layouts an operand tensor can have:
+    heads-major (B*H, N, d) [reference] or projection (B, N, H*d) [ProjView]"""
+
+    def __init__(self, q, k, heads, proj):
+        self.proj, self.h = proj, heads
+        if proj:
+            self.N, C = q.shape[1], q.shape[2]
+            self.Nk = k.shape[1]
+            self.d = C // heads
+            self.q = (C, self.d)
+            self.kv = (k.shape[2], self.d)
+        else:
+            self.N, self.d = q.shape[1], q.shape[2]
+            self.Nk = k.shape[1]
+            self.q = (self.d, self.N * self.d)
+            self.kv = (self.d, self.Nk * self.d)
+
+    def sl(self, t, i):
+        return t[i] if self.proj else t[i * self.h:(i + 1) * self.h]
+
+    def new_batch(self, like, entries, n_tokens):
+        """an uninitialised tensor of `entries` batch entries in this layout"""
+        if self.proj:
+            return torch.empty(entries, n_tokens, self.h * self.d, device=like.device, dtype=like.dtype)
+        return torch.empty(entries * self.h, n_tokens, self.d, device=like.device, dtype=like.dtype)
+
+    def strides(self, out=None):
+        o = self.q if out is None else out
+        return _lib.host_longs([self.q[0], self.q[1], self.kv[0], self.kv[1], o[0], o[1]])
+
+
+def attention_forward(qs, ks, vs, scale, dims=None, strides=None, want32=None, os=None, os_is_bf16=False):
+    """G query streams against their K/V slabs.  -> (O32, LSE): O32[g] (H,N,d) fp32 for the streams in `want32` (default: all) else None;
+    LSE (G,H,N) fp32.  `os[g]`: optional strided output slab per stream (bf16 / fp32), written by the kernel in the layout of q.
+    Without `dims`/`strides` the operands are contiguous (H,N,d) tensors."""
     G = len(qs)
-    H, N, d = qs[0].shape
-    Nk = ks[0].shape[1]
-    O = torch.empty(G, H, N, d, device=qs[0].device, dtype=torch.float32)
-    LSE = torch.empty(G, H, N, device=qs[0].device, dtype=torch.float32)
+    if dims is None:
+        H, N, d = qs[0].shape
+        Nk = ks[0].shape[1]
+    else:
+        H, N, Nk, d = dims
+    dev = qs[0].device
+    want32 = range(G) if want32 is None else want32
+    buf = torch.empty(len(want32), H, N, d, device=dev, dtype=torch.float32) if len(want32) else None
+    O32 = [None] * G
+    for i, g in enumerate(want32):
+        O32[g] = buf[i]
+    LSE = torch.empty(G, H, N, device=dev, dtype=torch.float32)
     entry = "gd_attn_fwd_generic"
     if _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024:
         entry = "gd_attn_fwd_sm100"
-    call(entry, _lib.ptr_array(qs), _lib.ptr_array(ks), _lib.ptr_array(vs), _lib.ptr_array([O[g] for g in range(G)]),
-         _lib.ptr_array([LSE[g] for g in range(G)]), G, H, N, Nk, d, float(scale), stream(), tag=(G, H, N, Nk, d))
-    return O, LSE
+    call(entry, _lib.ptr_array(qs), _lib.ptr_array(ks), _lib.ptr_array(vs), _lib.ptr_array(O32), _lib.ptr_array([LSE[g] for g in range(G)]),
+         _lib.ptr_array(os) if os is not None else None, G, H, N, Nk, d, float(scale), strides, int(os_is_bf16), stream(), tag=(G, H, N, Nk, d))
+    return O32, LSE
 
 
-def warp_queries(q_base, cache):
-    """q_base (H,N,d) bf16 -> q*(1-M) + M*splat(q)  (attention_processors.py:544), bf16"""
-    return geometry.splat_composite(q_base, cache.idx, cache.dist2, channels_last=True, blend_mask=cache.m_edit, out_dtype=torch.bfloat16)
+def warp_queries(q_base, cache, lay=None, out=None):
+    """q_base: one (H,N,d) bf16 slab -> q*(1-M) + M*splat(q)  (attention_processors.py:544), bf16, in the layout of q"""
+    if lay is None:
+        return geometry.splat_composite(q_base, cache.idx, cache.dist2, channels_last=True, blend_mask=cache.m_edit, out_dtype=torch.bfloat16)
+    st = _lib.host_longs(lay.q)
+    S = cache.S
+    r2 = float(geometry.np.float32(pow(geometry.splat_radius_ndc(S, None), 2)))
+    call("gd_splat_composite_rows", _lib.base_ptr(q_base), 1, st, ptr(cache.idx), ptr(cache.dist2), lay.h, lay.N, lay.d, cache.idx.shape[-1], r2,
+         float(geometry.SPLATTER.tau), ptr(cache.m_edit), 0, _lib.base_ptr(out), 1, st, stream())
+    return out
 
 
 class LayerSpec:
     """Static description of one controller call."""
     __slots__ = ("kind", "is_cross", "heads", "cb", "ce", "scale", "blend", "with_loss", "weights", "cache", "log_accum", "w_rem_dev")
-     # optional device scalar holding weights["removal"] (kept current by the controller; lets a captured pass follow the
-                         # adaptive schedule)
 
     def __init__(self, **kw):
         self.w_rem_dev = None   # optional device scalar holding weights["removal"], kept current by the controller: lets a captured pass
@@ -122,60 +193,68 @@ class LayerSpec:
             setattr(self, k, v)
 
 
-def _forward_impl(q, k, v, spec):
-    """Runs the fused layer.  Returns (out, terms6 or None, saved-for-backward dict or None)."""
+def _forward_impl(q, k, v, spec, proj=False):
+    """Runs the fused layer on q, k, v tensors in heads-major (B*H, N, d) or (proj) projection (B, N, H*d) layout.
+    Returns (out in the same layout, terms6 or None, saved-for-backward dict or None)."""
     h, (cb0, cb1), (ce0, ce1) = spec.heads, spec.cb, spec.ce
     assert ce1 - ce0 == 1 and cb1 - cb0 == 1
     cache = spec.cache
-    N, d = q.shape[1], q.shape[2]
-    Nk = k.shape[1]
+    lay = _Layout(q, k, h, proj)
+    N, d, Nk = lay.N, lay.d, lay.Nk
     qb, kb, vb = _bf16(q), _bf16(k), _bf16(v)
-    sl = lambda t, i: t[i * h:(i + 1) * h]
+    sl = lay.sl
+    bp = _lib.base_ptr
     qs = [sl(qb, i) for i in range(cb1)]
     ks = [sl(kb, i) for i in range(cb1)]
     vs = [sl(vb, i) for i in range(cb1)]
     q_e = sl(qb, ce0)
+    assert q.dtype in (torch.bfloat16, torch.float32)
+    is_bf16 = q.dtype == torch.bfloat16
+    out = lay.new_batch(q, cb1 + 1, N)                   # plain entries 0..cb1-1, then the edit entry
+    os = [sl(out, i) for i in range(cb1)]                # plain streams: written by the attention kernel itself, in place, in q's dtype
+    q_w = None
     if spec.kind == "edit":
-        q_w = warp_queries(sl(qb, cb0), cache)
+        q_w = warp_queries(sl(qb, cb0), cache, lay, lay.new_batch(qb, 1, N))
         k_e = sl(kb, ce0) if spec.is_cross else sl(kb, cb0)
-        qs += [q_w, q_e]
+        qs += [sl(q_w, 0), q_e]
         ks += [sl(kb, cb0), k_e]
         vs += [sl(vb, cb0), sl(vb, cb0)]
         g_e = cb1 + 1
+        want32 = [cb1, cb1 + 1]
     else:
         k_e = sl(kb, cb0)
         qs += [q_e]
         ks += [k_e]
         vs += [sl(vb, cb0)]
         g_e = cb1
+        want32 = [cb0, cb1]
         if not spec.blend:
             qs += [q_e]
             ks += [sl(kb, ce0)]
             vs += [sl(vb, ce0)]
-    O, LSE = attention_forward(qs, ks, vs, spec.scale)
+            want32.append(cb1 + 1)
+    os += [None] * (len(qs) - cb1)
+    O, LSE = attention_forward(qs, ks, vs, spec.scale, dims=(h, N, Nk, d), strides=lay.strides(), want32=want32, os=os, os_is_bf16=is_bf16)
     r = O[g_e]
     e = O[cb1] if spec.kind == "edit" else O[cb0]
-    out = torch.empty(cb1 * h + h, N, d, device=q.device, dtype=q.dtype)
-    out[:cb1 * h] = O[:cb1].reshape(cb1 * h, N, d)
-    out_edit = out[cb1 * h:]
-    is_bf16 = q.dtype == torch.bfloat16
-    assert q.dtype in (torch.bfloat16, torch.float32)
+    out_edit = sl(out, cb1)
+    ost = _lib.host_longs(lay.q)
     if spec.kind == "edit":
         if spec.blend:
             coef = cache.one_minus_m_edit
-            call("gd_blend_rows", ptr(e), ptr(cache.m_edit), ptr(r), ptr(coef), h, N, d, ptr(out_edit), int(is_bf16), stream())
+            call("gd_blend_rows", ptr(e), ptr(cache.m_edit), ptr(r), ptr(coef), h, N, d, bp(out_edit), int(is_bf16), ost, stream())
         else:
             coef = None
-            call("gd_blend_rows", None, None, ptr(r), None, h, N, d, ptr(out_edit), int(is_bf16), stream())
+            call("gd_blend_rows", None, None, ptr(r), None, h, N, d, bp(out_edit), int(is_bf16), ost, stream())
     else:
         if spec.blend:
             coef = cache.m_inp_plus_bg
-            call("gd_blend_rows", None, None, ptr(r), ptr(coef), h, N, d, ptr(out_edit), int(is_bf16), stream())
+            call("gd_blend_rows", None, None, ptr(r), ptr(coef), h, N, d, bp(out_edit), int(is_bf16), ost, stream())
         else:
             coef = cache.m_bg
-            call("gd_blend_rows", ptr(O[g_e + 1]), ptr(cache.m_inp), ptr(r), ptr(coef), h, N, d, ptr(out_edit), int(is_bf16), stream())
+            call("gd_blend_rows", ptr(O[g_e + 1]), ptr(cache.m_inp), ptr(r), ptr(coef), h, N, d, bp(out_edit), int(is_bf16), ost, stream())
     saved = dict(q_e=q_e, k_e=k_e, v_e=sl(vb, cb0), o_e=r, lse_e=LSE[g_e], g_loss=None, extra=None, delta_extra=None, coef=coef,
-                 ld=(Nk + 7) // 8 * 8, M=0)
+                 ld=(Nk + 7) // 8 * 8, M=0, lay=lay, keep=(qb, kb, vb, q_w))
     if not spec.with_loss:
         return out, None, saved
 
@@ -209,10 +288,11 @@ def _forward_impl(q, k, v, spec):
     rem_terms = extra = delta_extra = None
     ld = (Nk + 7) // 8 * 8
     if M > 0:
+        qk_st = _lib.host_longs([lay.q[0], lay.q[1], lay.kv[0], lay.kv[1]])
         a_b = torch.empty(h, N, ld, device=dev, dtype=torch.bfloat16)
-        call("gd_attn_probs", ptr(sl(qb, cb0)), ptr(sl(kb, cb0)), ptr(LSE[cb0]), None, N, h, N, Nk, d, float(spec.scale), ptr(a_b), ld, stream())
+        call("gd_attn_probs", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), None, N, h, N, Nk, d, float(spec.scale), ptr(a_b), ld, qk_st, stream())
         a_e = torch.empty(h, M, ld, device=dev, dtype=torch.bfloat16)
-        call("gd_attn_probs", ptr(q_e), ptr(k_e), ptr(LSE[g_e]), ptr(cache.rows), M, h, N, Nk, d, float(spec.scale), ptr(a_e), ld, stream())
+        call("gd_attn_probs", bp(q_e), bp(k_e), ptr(LSE[g_e]), ptr(cache.rows), M, h, N, Nk, d, float(spec.scale), ptr(a_e), ld, qk_st, stream())
         n_tiles = (N + 63) // 64
         partial = torch.empty(h, n_tiles, M, 4, device=dev, dtype=torch.float32)
         call("gd_corr_max_partial", ptr(a_e), ptr(a_b), h, M, N, Nk, ld, ptr(cache.m_inp), ptr(cache.m_bg), ptr(partial), stream())
@@ -238,8 +318,8 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
     """(q, k, v) -> (out, terms[6]); terms[5] is the weighted layer loss (differentiable), terms[0:5] the logged terms."""
 
     @staticmethod
-    def forward(ctx, q, k, v, spec):
-        out, terms, saved = _forward_impl(q, k, v, spec)
+    def forward(ctx, q, k, v, spec, proj):
+        out, terms, saved = _forward_impl(q, k, v, spec, proj)
         ctx.spec, ctx.saved_dict = spec, saved
         ctx.shapes = (q.shape, k.shape, q.dtype, k.dtype)
         if terms is None:
@@ -252,17 +332,20 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
         spec, s = ctx.spec, ctx.saved_dict
         h, (cb0, cb1), (ce0, ce1) = spec.heads, spec.cb, spec.ce
         q_shape, k_shape, q_dtype, k_dtype = ctx.shapes
-        N, d = q_shape[1], q_shape[2]
-        Nk = k_shape[1]
+        lay = s["lay"]
+        N, d, Nk = lay.N, lay.d, lay.Nk
+        bp = _lib.base_ptr
         dev = s["q_e"].device
         if spec.kind != "edit" and not spec.blend:
             raise NotImplementedError("gradient through the remover's identity branch is never requested by the reference loop "
                                       "(optimisation ends before obj_edit_step, editor.py:189)")
         g_out = None
         if d_out is not None:
-            g_out = d_out[cb1 * h:].contiguous()
-            if g_out.dtype not in (torch.bfloat16, torch.float32):
-                g_out = g_out.float()
+            if d_out.dtype not in (torch.bfloat16, torch.float32):
+                d_out = d_out.float()
+            if not d_out.is_contiguous():
+                d_out = d_out.contiguous()
+            g_out = lay.sl(d_out, cb1)
         has_loss = s["g_loss"] is not None and d_terms is not None
         d_loss = d_terms[5:6].to(torch.float32).contiguous() if has_loss else None
         M = s["M"] if has_loss else 0
@@ -271,56 +354,65 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
         extra = ptr(s["extra"]) if has_extra else None
         dq = torch.zeros(q_shape, device=dev, dtype=q_dtype)
         if g_out is None and not has_loss:
-            return dq, None, None, None
+            return dq, None, None, None, None
         d_o = torch.empty(h, N, d, device=dev, dtype=torch.bfloat16)
         delta = torch.empty(h, N, device=dev, dtype=torch.float32)
-        call("gd_attn_bwd_prep", ptr(g_out), int(g_out is not None and g_out.dtype == torch.bfloat16), ptr(s["coef"]),
+        call("gd_attn_bwd_prep", bp(g_out), int(g_out is not None and g_out.dtype == torch.bfloat16), _lib.host_longs(lay.q), ptr(s["coef"]),
              ptr(s["g_loss"]) if has_loss else None, ptr(d_loss), ptr(s["o_e"]), ptr(s["delta_extra"]) if has_extra else None, rowmap, M,
              h, N, d, ptr(d_o), ptr(delta), stream())
-        dq_e = torch.empty(h, N, d, device=dev, dtype=torch.float32)
+        # dQ of the edit entry is written by the kernel straight into its slab of the full gradient tensor, in q's layout and dtype
+        dq_is_bf16 = int(q_dtype == torch.bfloat16)
         if _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024 and s["ld"] % 4 == 0:
-            call("gd_attn_bwd_sm100", ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dq_e), h, N, d, float(spec.scale), stream(), tag=(h, N, d))
+            call("gd_attn_bwd_sm100", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
+                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dq, ce0)), h, N, d, float(spec.scale), lay.strides(), dq_is_bf16,
+                 stream(), tag=(h, N, d))
         else:
-            call("gd_attn_bwd", 0, ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dq_e), h, N, Nk, d, float(spec.scale), stream())
-        dq[ce0 * h:ce1 * h] = dq_e.to(q_dtype)
+            call("gd_attn_bwd", 0, bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
+                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dq, ce0)), h, N, Nk, d, float(spec.scale), lay.strides(),
+                 dq_is_bf16, stream())
         dk = None
         if spec.is_cross and spec.kind == "edit":
-            dk_e = torch.empty(h, Nk, d, device=dev, dtype=torch.float32)
+            dk = torch.zeros(k_shape, device=dev, dtype=k_dtype)
             # Nk = 77 -> two key tiles per head: split the query walk so the grid fills the 148 SMs (fixed-order partial sums)
             splits = max(1, min((N + 63) // 64, (2 * 148) // (h * ((Nk + 63) // 64))))
             ws = torch.empty(splits, h, Nk, d, device=dev, dtype=torch.float32) if splits > 1 else None
-            call("gd_attn_bwd_dk_split", ptr(s["q_e"]), ptr(s["k_e"]), ptr(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, ptr(dk_e), ptr(ws), splits, h, N, Nk, d, float(spec.scale), stream())
-            dk = torch.zeros(k_shape, device=dev, dtype=k_dtype)
-            dk[ce0 * h:ce1 * h] = dk_e.to(k_dtype)
-        return dq, dk, None, None
+            call("gd_attn_bwd_dk_split", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
+                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dk, ce0)), ptr(ws), splits, h, N, Nk, d, float(spec.scale),
+                 lay.strides(out=lay.kv), int(k_dtype == torch.bfloat16), stream())
+        return dq, dk, None, None, None
 
 
 def shared_attention_layer(q, k, v, spec):
-    """-> (out, loss or None, terms or None).  Differentiable w.r.t. the edit sample's q (and k for cross layers) whenever autograd
-    is recording; the loss exists only when spec.with_loss."""
+    """-> (out, loss or None, terms or None).  q, k, v: heads-major (B*H, N, d) tensors (the reference's layout) or ProjViews; `out` comes
+    back in the same layout (a ProjView input returns the plain (B, N, H*d) tensor).  Differentiable w.r.t. the edit sample's q (and k
+    for cross layers) whenever autograd is recording; the loss exists only when spec.with_loss."""
+    proj = isinstance(q, ProjView)
+    if proj:
+        q, k, v = q.t, k.t, v.t
     if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad):
-        out, terms = _SharedAttentionLayerFn.apply(q, k, v, spec)
+        out, terms = _SharedAttentionLayerFn.apply(q, k, v, spec, proj)
         if spec.with_loss:
             return out, terms[5], terms
         return out, None, None
-    out, terms, _ = _forward_impl(q, k, v, spec)
+    out, terms, _ = _forward_impl(q, k, v, spec, proj)
     return out, (terms[5] if terms is not None else None), terms
 
 
 def plain_attention(q, k, v, scale, heads):
-    """softmax(scale q k^T) v for (B*H, N, d) tensors: VanillaAttentionProcessor / outside the replace window
-    (attention_processors.py:120-121, 646-647).  Forward only."""
-    BH, N, d = q.shape
-    B = BH // heads
+    """softmax(scale q k^T) v for (B*H, N, d) tensors or ProjViews: VanillaAttentionProcessor / outside the replace window
+    (attention_processors.py:120-121, 646-647).  Forward only.  The kernel writes the result in q's dtype and layout."""
+    proj = isinstance(q, ProjView)
+    if proj:
+        q, k, v = q.t, k.t, v.t
+    lay = _Layout(q, k, heads, proj)
+    B = q.shape[0] if proj else q.shape[0] // heads
+    assert q.dtype in (torch.bfloat16, torch.float32)
     qb, kb, vb = _bf16(q), _bf16(k), _bf16(v)
-    outs = []
+    out = lay.new_batch(q, B, lay.N)
     for g0 in range(0, B, 8):
         g1 = min(B, g0 + 8)
-        sl = lambda t, i: t[i * heads:(i + 1) * heads]
-        O, _ = attention_forward([sl(qb, i) for i in range(g0, g1)], [sl(kb, i) for i in range(g0, g1)], [sl(vb, i) for i in range(g0, g1)], scale)
-        outs.append(O.reshape((g1 - g0) * heads, N, d))
-    O = outs[0] if len(outs) == 1 else torch.cat(outs)
-    return O.to(q.dtype)
+        rng = range(g0, g1)
+        attention_forward([lay.sl(qb, i) for i in rng], [lay.sl(kb, i) for i in rng], [lay.sl(vb, i) for i in rng], scale,
+                          dims=(heads, lay.N, lay.Nk, lay.d), strides=lay.strides(), want32=[], os=[lay.sl(out, i) for i in rng],
+                          os_is_bf16=q.dtype == torch.bfloat16)
+    return out

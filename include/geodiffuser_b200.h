@@ -50,6 +50,13 @@ int gd_splat_index(const float* coords, int B, int S, float radius_ndc, int K, i
 int gd_splat_composite(const void* src, int src_dtype, int layout, const int* idx, const float* dist2, int Bi, int B, int P, int C,
                        int K, float r2, float tau, const float* blend_mask, int post, void* out, int out_dtype, void* stream);
 
+/* The per-layer query warp (attention_processors.py:363,424,544: the same index for all heads) on one (B = heads, P, C = head_dim) slab
+ * with explicit element strides: element (b, p, c) at base + b*head + p*row + c; *_strides_host = {row, head} (NULL: contiguous (B,P,C)).
+ * One warp per output pixel; same arithmetic as gd_splat_composite, bit for bit. */
+int gd_splat_composite_rows(const void* src, int src_dtype, const long* src_strides_host, const int* idx, const float* dist2, int B, int P,
+                            int C, int K, float r2, float tau, const float* blend_mask, int post, void* out, int out_dtype,
+                            const long* out_strides_host, void* stream);
+
 /* warp_utils.py:364-399 get_mesh + :235-298 splatter_mesh (pytorch3d rasterize_meshes): coverage of the object's depth mesh. */
 int gd_mesh_mask(const float* coords, const float* mask, int H, int W, float blur, float* out, void* stream);
 
@@ -59,14 +66,22 @@ int gd_morph(const float* src, int B, int H, int W, int kernel, int mode, float*
 /* ---- (2) shared attention forward ---------------------------------------------------------------------------------- */
 
 /* attention_sharing.py:30-47 compute_attention + torch.bmm(P,V) (attention_processors.py:427-433, 548-557, 643-647).
- * G query streams q[g] (H,N,d) bf16, each against k[g], v[g] (H,Nk,d) bf16 -> o[g] (H,N,d) fp32, lse[g] (H,N) fp32 (natural log).
- * The five arrays are HOST arrays of G device pointers; G <= 8; d % 8 == 0, d <= 160.  Any N, Nk. */
+ * G query streams q[g], each an (H,N,d) bf16 SLAB, against k[g], v[g] (H,Nk,d) bf16 slabs.  A slab is addressed as
+ * base + h*head_stride + n*row_stride + c (element strides, multiples of 8): strides_host = {q_row, q_head, kv_row, kv_head, os_row, os_head};
+ * NULL = contiguous (H,N,d), the reference's head_to_batch_dim layout (attention_sharing.py:210-242).  The projection layout (N, H*d) that
+ * to_q / to_k / to_v produce is {H*d, d}: it is read in place, so neither head_to_batch_dim nor batch_to_head_dim copies anything.
+ * Outputs per stream: o[g] (H,N,d) fp32 contiguous (feeds the loss terms) and / or os[g], a strided slab (bf16 if os_is_bf16 else fp32) --
+ * at least one of the two; lse[g] (H,N) fp32 (natural log).  The pointer arrays are HOST arrays of G device pointers (os_host may be NULL);
+ * G <= 8; d % 8 == 0, d <= 160.  Any N, Nk. */
 int gd_attn_fwd_generic(const void* const* q_host, const void* const* k_host, const void* const* v_host, void* const* o_host,
-                        void* const* lse_host, int G, int H, int N, int Nk, int d, float scale, void* stream);
+                        void* const* lse_host, void* const* os_host, int G, int H, int N, int Nk, int d, float scale,
+                        const long* strides_host, int os_is_bf16, void* stream);
 
-/* Same contract, tcgen05 / TMEM / TMA kernel for the large self-attention levels: N == Nk, N % 128 == 0, d in {40, 80}. */
+/* Same contract, tcgen05 / TMEM / TMA kernel for the large self-attention levels: N == Nk, N % 128 == 0, d in {40, 80}
+ * (operands are 3-D TMA tensors (d, N, H) with the strides above). */
 int gd_attn_fwd_sm100(const void* const* q_host, const void* const* k_host, const void* const* v_host, void* const* o_host,
-                      void* const* lse_host, int G, int H, int N, int Nk, int d, float scale, void* stream);
+                      void* const* lse_host, void* const* os_host, int G, int H, int N, int Nk, int d, float scale,
+                      const long* strides_host, int os_is_bf16, void* stream);
 
 /* Tuning knob of gd_attn_fwd_sm100 (process-wide, not part of the reference surface): poly in {0,2,3,4,6,8} = every poly-th exponential
  * of the online softmax is evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (0 = all MUFU; default 4). */
@@ -75,36 +90,41 @@ int gd_attn_sm100_config(int poly);
 /* ---- (3) backward, fused with the attention-map losses --------------------------------------------------------------- */
 
 /* dO = g_out * coef[row] + g_loss * (*loss_scale) (bf16 out), delta[h,row] = sum_c dO*O (+ delta_extra[h, rowmap[row]] * *loss_scale).
- * g_out (H,N,d) fp32/bf16 or NULL; coef (N) or NULL; g_loss (H,N,d) fp32 or NULL; loss_scale: device scalar or NULL (=1). */
-int gd_attn_bwd_prep(const void* g_out, int g_out_is_bf16, const float* coef, const float* g_loss, const float* loss_scale,
-                     const float* o, const float* delta_extra, const int* rowmap, int M, int H, int N, int d, void* d_o_bf16,
-                     float* delta, void* stream);
+ * g_out: (H,N,d) slab fp32/bf16, g_strides_host = {row, head} (NULL: contiguous), or NULL; coef (N) or NULL; g_loss (H,N,d) fp32 or NULL;
+ * loss_scale: device scalar or NULL (=1). */
+int gd_attn_bwd_prep(const void* g_out, int g_out_is_bf16, const long* g_strides_host, const float* coef, const float* g_loss,
+                     const float* loss_scale, const float* o, const float* delta_extra, const int* rowmap, int M, int H, int N, int d,
+                     void* d_o_bf16, float* delta, void* stream);
 
-/* What torch autograd derives for softmax(scale q k^T) v (attention_sharing.py:35-45).  mode 0: out = dQ (H,N,d); mode 1: out = dK
- * (H,Nk,d).  extra (H,M,ex_ld) fp32 = dL/dP rows for the queries with rowmap[row] >= 0 (removal loss), scaled by *extra_scale. */
+/* What torch autograd derives for softmax(scale q k^T) v (attention_sharing.py:35-45).  mode 0: out = dQ, a slab like q; mode 1: out = dK,
+ * a slab like k.  q, k, v slabs with strides_host = {q_row, q_head, kv_row, kv_head, out_row, out_head} (NULL: contiguous); d_o (H,N,d) bf16
+ * contiguous; out fp32 or bf16 (out_is_bf16).  extra (H,M,ex_ld) fp32 = dL/dP rows for the queries with rowmap[row] >= 0 (removal loss),
+ * scaled by *extra_scale. */
 int gd_attn_bwd(int mode, const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
-                const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* out, int H, int N, int Nk,
-                int d, float scale, void* stream);
+                const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* out, int H, int N, int Nk,
+                int d, float scale, const long* strides_host, int out_is_bf16, void* stream);
 
 /* dK exactly as gd_attn_bwd mode 1, but with the query range split `splits` ways across the grid (cross layers: Nk = 77 gives only two
  * 64-key tiles per head, so one CTA per tile would walk all N queries serially).  workspace: >= splits * H * Nk * d floats; the partial
  * sums are added in ascending split order, so the result is deterministic.  splits <= 1 or workspace == NULL falls back to mode 1. */
 int gd_attn_bwd_dk_split(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
-                         const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* dk, float* workspace,
-                         int splits, int H, int N, int Nk, int d, float scale, void* stream);
+                         const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* dk, float* workspace,
+                         int splits, int H, int N, int Nk, int d, float scale, const long* strides_host, int out_is_bf16, void* stream);
 
 /* Same operands and result as gd_attn_bwd mode 0 (dQ), tcgen05 / TMEM / TMA kernel for the self-attention levels:
  * N == Nk, N % 128 == 0, d in {40, 80}; extra rows (if any) 16-byte aligned (ex_ld % 4 == 0). */
 int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
-                      const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, float* dq, int H, int N,
-                      int d, float scale, void* stream);
+                      const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* dq, int H, int N,
+                      int d, float scale, const long* strides_host, int dq_is_bf16, void* stream);
 
-int gd_cast_f32_to_bf16(const float* src, void* dst_bf16, long n, void* stream);
+/* fp32 -> bf16 */
+int gd_cast_f32_to_bf16(const float* src, void* dst, long n, void* stream);
 
-/* P[h,m,:] = softmax row of q[h, rows[m] or m] against k[h] given lse (bf16 out, row stride ldp % 8 == 0, pad columns zero).
- * Materialises the maps removal_loss_geodiff consumes (attention_processors.py:250). */
+/* attention_processors.py:250-252: the base attention map A_b = softmax(scale q_b k_b^T) and the inpaint rows of the edit map, materialised
+ * in bf16 from the stored lse: P[h, m, :] for query rows[m] (or m if rows == NULL); row stride ldp (multiple of 8, >= Nk, pad columns zero).
+ * q, k slabs with qk_strides_host = {q_row, q_head, k_row, k_head} (NULL: contiguous). */
 int gd_attn_probs(const void* q, const void* k, const float* lse, const int* rows, int M, int H, int N, int Nk, int d, float scale,
-                  void* p_out_bf16, int ldp, void* stream);
+                  void* p_out, int ldp, const long* qk_strides_host, void* stream);
 
 /* attention_processors.py:250-258: corr = A_e[rows] A_b^T, masked max / arg-max per 64-wide tile of columns.
  * partial (H, ceil(Nb/64), M, 4) = {max_in, argmax_in (int bits), max_bg, argmax_bg (int bits)}. */
@@ -137,9 +157,10 @@ int gd_amodal_knn(const float* m_edit, int S, int* idx4, float* val4, float* w, 
 int gd_amodal_target(const float* e, const float* m_edit, const int* idx4, const float* val4, const float* gauss25_host, int H, int S,
                      int d, float* scratch, float* target, void* stream);
 
-/* attention_processors.py:617-624, 922-925: out = a * ma[row] + b * mb[row] (a may be NULL; mb NULL = 1). */
+/* attention_processors.py:617-624, 922-925: out = a * ma[row] + b * mb[row] (a may be NULL; mb NULL = 1); a, b (H,N,d) fp32 contiguous,
+ * out a slab with out_strides_host = {row, head} (NULL: contiguous). */
 int gd_blend_rows(const float* a, const float* ma, const float* b, const float* mb, int H, int N, int d, void* out, int out_is_bf16,
-                  void* stream);
+                  const long* out_strides_host, void* stream);
 
 /* ---- (4) DDIM step and latent update ------------------------------------------------------------------------------- */
 

@@ -48,7 +48,7 @@ def fwd_case(entry, G, H, N, d, check=True):
 
     def run():
         call(entry, _lib.ptr_array(qs), _lib.ptr_array(ks), _lib.ptr_array(vs), _lib.ptr_array([O[i] for i in range(G)]),
-             _lib.ptr_array([L[i] for i in range(G)]), G, H, N, N, d, float(scale), stream())
+             _lib.ptr_array([L[i] for i in range(G)]), None, G, H, N, N, d, float(scale), None, 0, stream())
 
     ms = timed(run, iters)
     fl = 4.0 * G * H * N * N * d
@@ -68,8 +68,8 @@ def bwd_case(H, N, d, M=0, sm100=False):
     O = torch.empty(1, H, N, d, device="cuda", dtype=torch.float32)
     L = torch.empty(1, H, N, device="cuda", dtype=torch.float32)
     entry = "gd_attn_fwd_sm100" if (N % 128 == 0 and d in (40, 80)) else "gd_attn_fwd_generic"
-    call(entry, _lib.ptr_array([q]), _lib.ptr_array([k]), _lib.ptr_array([v]), _lib.ptr_array([O[0]]), _lib.ptr_array([L[0]]), 1, H, N, N, d,
-         float(scale), stream())
+    call(entry, _lib.ptr_array([q]), _lib.ptr_array([k]), _lib.ptr_array([v]), _lib.ptr_array([O[0]]), _lib.ptr_array([L[0]]), None, 1, H, N, N, d,
+         float(scale), None, 0, stream())
     delta = (do.float() * O[0]).sum(-1).contiguous()
     dq = torch.empty(H, N, d, device="cuda", dtype=torch.float32)
     ld = (N + 7) // 8 * 8
@@ -84,10 +84,10 @@ def bwd_case(H, N, d, M=0, sm100=False):
     def run():
         if sm100:
             call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N,
-                 d, float(scale), stream())
+                 d, float(scale), None, 0, stream())
         else:
             call("gd_attn_bwd", 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N,
-                 d, float(scale), stream())
+                 d, float(scale), None, 0, stream())
 
     ms = timed(run, iters)
     fl = 6.0 * H * N * N * d

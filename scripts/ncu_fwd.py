@@ -15,5 +15,5 @@ k, v = mk(), mk()
 O = torch.empty(G, H, N, d, device="cuda"); L = torch.empty(G, H, N, device="cuda")
 for _ in range(3):
     call("gd_attn_fwd_sm100", _lib.ptr_array(qs), _lib.ptr_array([k] * G), _lib.ptr_array([v] * G), _lib.ptr_array([O[i] for i in range(G)]),
-         _lib.ptr_array([L[i] for i in range(G)]), G, H, N, N, d, d ** -0.5, stream())
+         _lib.ptr_array([L[i] for i in range(G)]), None, G, H, N, N, d, d ** -0.5, None, 0, stream())
 torch.cuda.synchronize()

@@ -53,28 +53,42 @@ def make_controller(kind, geo, cur_step, use_cfg):
     return c
 
 
+@pytest.mark.parametrize("layout", ["heads", "proj"])
 @pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
-def test_controller_matches_reference_golden(case):
+def test_controller_matches_reference_golden(case, layout):
+    """layout "heads": q, k, v as the reference hands them to the controller, (B*H, N, d); "proj": the same values as functional.ProjView of
+    the projection output (B, N, H*d) -- what the processors of this package pass (no head permute copies).  Same goldens for both."""
+    from geodiffuser_b200 import functional as Fn
+
     name, gname, kind, S, H, d, is_cross, use_cfg, seed, cur_step = case
     z = np.load(os.path.join(GOLDEN, f"attn_{name}.npz"))
     geo = geometry_for(gname)
     c = make_controller(kind, geo, cur_step, use_cfg)
     B = 4 if use_cfg else 2
     q, k, v = synth.qkv(seed, B, H, S * S, 77 if is_cross else S * S, d)
-    q, k, v = (torch.from_numpy(a).cuda().requires_grad_(not use_cfg) for a in (q, k, v))
+    q, k, v = (torch.from_numpy(a).cuda() for a in (q, k, v))
+    to_proj = lambda t: t.reshape(B, H, t.shape[1], d).permute(0, 2, 1, 3).reshape(B, t.shape[1], H * d).contiguous()
+    to_heads = lambda t: t.reshape(B, t.shape[1], H, d).permute(0, 2, 1, 3).reshape(B * H, t.shape[1], d)
+    if layout == "proj":
+        q, k, v = to_proj(q), to_proj(k), to_proj(v)
+    q, k, v = (t.requires_grad_(not use_cfg) for t in (q, k, v))
+    args = (Fn.ProjView(q, H), Fn.ProjView(k, H), Fn.ProjView(v, H)) if layout == "proj" else (q, k, v)
     with torch.set_grad_enabled(not use_cfg):
-        out = c(q, k, v, is_cross, "down", transform_coords=geo["coords"], scale=d ** -0.5, mask=None)
+        out = c(*args, is_cross, "down", transform_coords=geo["coords"], scale=d ** -0.5, mask=None)
     assert out.shape == q.shape
-    assert relerr(out.detach().float().cpu().numpy(), z["out"]) <= TOL
+    out_h = to_heads(out) if layout == "proj" else out
+    assert relerr(out_h.detach().float().cpu().numpy(), z["out"]) <= TOL
     assert c.cur_att_layer == 1
     if "loss" in z.files:
         loss = c.loss
-        assert abs(float(loss) - float(z["loss"])) <= TOL * abs(float(z["loss"])) + 1e-3
+        assert abs(float(loss.detach()) - float(z["loss"])) <= TOL * abs(float(z["loss"])) + 1e-3
         att = "cross" if is_cross else "self"
         for key, val in c.loss_log_dict[att].items():
             ref = float(z["term_" + key])
             assert abs(float(val) - ref) <= TOL * max(abs(ref), 0.05), (key, float(val), ref)
         gq, gk = torch.autograd.grad(loss + 0.37 * out.float().sum(), [q, k], allow_unused=True)
+        if layout == "proj":
+            gq, gk = to_heads(gq), (to_heads(gk) if gk is not None else None)
         # The golden gradient also holds d(0.37*sum(out_base))/dq_base through the plain branch; inside the UNet nothing downstream of
         # the loss depends on the base sample (every base q/k/v is detached, attention_sharing.py:242), so the product path returns
         # exact zeros there and parity is judged on the edit half, which is what reaches latents[-1] / context[-1] (optimization.py:230-245).
@@ -152,13 +166,13 @@ def test_cross_layer_dk_split_matches_unsplit_and_fp32(N, Nk, d, M, splits):
     ref = torch.einsum("hnk,hnd->hkd", p * (dp - delta[..., None]), q.float()) * scale
     dk0 = torch.full((H, Nk, d), float("nan"), device="cuda")
     call("gd_attn_bwd", 1, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dk0), H, N, Nk, d,
-         float(scale), stream())
+         float(scale), None, 0, stream())
     outs = []
     for _ in range(2):
         dk = torch.full((H, Nk, d), float("nan"), device="cuda")
         ws = torch.full((splits, H, Nk, d), float("nan"), device="cuda")
         call("gd_attn_bwd_dk_split", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dk), ptr(ws),
-             splits, H, N, Nk, d, float(scale), stream())
+             splits, H, N, Nk, d, float(scale), None, 0, stream())
         torch.cuda.synchronize()
         outs.append(dk)
     assert torch.isfinite(outs[0]).all()

@@ -17,7 +17,7 @@ def _run(entry, qs, ks, vs, scale):
     O = torch.empty(G, H, N, d, device="cuda", dtype=torch.float32)
     L = torch.empty(G, H, N, device="cuda", dtype=torch.float32)
     call(entry, _lib.ptr_array(qs), _lib.ptr_array(ks), _lib.ptr_array(vs), _lib.ptr_array([O[g] for g in range(G)]),
-         _lib.ptr_array([L[g] for g in range(G)]), G, H, N, N, d, float(scale), stream())
+         _lib.ptr_array([L[g] for g in range(G)]), None, G, H, N, N, d, float(scale), None, 0, stream())
     torch.cuda.synchronize()
     return O, L
 
@@ -103,12 +103,64 @@ def test_sm100_backward_dq(N, d, H, M):
         dq = torch.full((H, N, d), float("nan"), device="cuda", dtype=torch.float32)
         if entry == "gd_attn_bwd":
             call(entry, 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N, d,
-                 float(scale), stream())
+                 float(scale), None, 0, stream())
         else:
             call(entry, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, d, float(scale),
-                 stream())
+                 None, 0, stream())
         torch.cuda.synchronize()
         out.append(dq)
     assert torch.isfinite(out[0]).all()
     assert relerr(out[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2       # bf16 operands / bf16 dS vs fp32 math (tolerance of the path: 2e-2)
     assert relerr(out[0].cpu().numpy(), out[1].cpu().numpy()) <= 1e-2
+
+
+@pytest.mark.parametrize("N,Nk,d,H", [(4096, 4096, 40, 8), (1024, 1024, 80, 8), (256, 256, 160, 8), (1024, 77, 80, 8), (200, 77, 40, 4)])
+@pytest.mark.timeout(120)
+def test_projection_layout_is_read_and_written_in_place(N, Nk, d, H):
+    """q / k / v as the projections produce them, (B, N, H*d), addressed through slab strides (no head_to_batch_dim copy), and the output /
+    dQ / dK written straight into (B, N, H*d) tensors (no batch_to_head_dim copy): bit-identical to the same kernels on the permuted,
+    contiguous (B*H, N, d) tensors, forward (bf16 strided output + fp32 output + lse) and backward."""
+    from geodiffuser_b200 import _lib, functional as Fn
+    from geodiffuser_b200._lib import call, ptr, stream
+
+    B = 2
+    g = torch.Generator(device="cuda").manual_seed(N + d)
+    qp = (torch.randn(B, N, H * d, device="cuda", generator=g) * 1.5).bfloat16()
+    kp = (torch.randn(B, Nk, H * d, device="cuda", generator=g) * 1.5).bfloat16()
+    vp = (torch.randn(B, Nk, H * d, device="cuda", generator=g) * 1.5).bfloat16()
+    perm = lambda t: t.reshape(t.shape[0], t.shape[1], H, d).permute(0, 2, 1, 3).reshape(t.shape[0] * H, t.shape[1], d).contiguous()
+    unperm = lambda t: t.reshape(B, H, t.shape[1], d).permute(0, 2, 1, 3).reshape(B, t.shape[1], H * d)
+    scale = d ** -0.5
+    out_p = Fn.plain_attention(Fn.ProjView(qp, H), Fn.ProjView(kp, H), Fn.ProjView(vp, H), scale, H)
+    out_h = Fn.plain_attention(perm(qp), perm(kp), perm(vp), scale, H)
+    assert out_p.shape == (B, N, H * d) and out_p.dtype == torch.bfloat16
+    assert torch.equal(out_p, unperm(out_h))
+    s = torch.einsum("bhnd,bhkd->bhnk", perm(qp).float().reshape(B, H, N, d), perm(kp).float().reshape(B, H, Nk, d)) * scale
+    ref = torch.softmax(s, -1) @ perm(vp).float().reshape(B, H, Nk, d)
+    assert relerr(out_h.float().cpu().numpy(), ref.reshape(B * H, N, d).cpu().numpy()) <= 1.5e-2
+
+    # backward entry points: dQ (and dK for Nk != N) of batch entry 1, strided bf16 outputs vs contiguous fp32 outputs
+    lay_p, lay_h = Fn._Layout(qp, kp, H, True), Fn._Layout(perm(qp), perm(kp), H, False)
+    qh, kh, vh = perm(qp), perm(kp), perm(vp)
+    O, L = Fn.attention_forward([lay_h.sl(qh, 1)], [lay_h.sl(kh, 1)], [lay_h.sl(vh, 1)], scale)
+    do = torch.randn(H, N, d, device="cuda", generator=g).bfloat16()
+    delta = (do.float() * O[0]).sum(-1).contiguous()
+    sm100 = Nk == N and N % 128 == 0 and d in (40, 80)
+    res = {}
+    for name, lay, (q_, k_, v_) in (("proj", lay_p, (qp, kp, vp)), ("heads", lay_h, (qh, kh, vh))):
+        dq = torch.zeros_like(q_)
+        args = (_lib.base_ptr(lay.sl(q_, 1)), _lib.base_ptr(lay.sl(k_, 1)), _lib.base_ptr(lay.sl(v_, 1)), ptr(do), ptr(L[0]), ptr(delta), None,
+                None, None, (Nk + 7) // 8 * 8, 0, _lib.base_ptr(lay.sl(dq, 1)))
+        if sm100:
+            call("gd_attn_bwd_sm100", *args, H, N, d, float(scale), lay.strides(), 1, stream())
+        else:
+            call("gd_attn_bwd", 0, *args, H, N, Nk, d, float(scale), lay.strides(), 1, stream())
+        dk = torch.zeros_like(k_)
+        ws = torch.empty(4, H, Nk, d, device="cuda")
+        call("gd_attn_bwd_dk_split", *args[:11], _lib.base_ptr(lay.sl(dk, 1)), ptr(ws), 4, H, N, Nk, d, float(scale), lay.strides(out=lay.kv), 1,
+             stream())
+        torch.cuda.synchronize()
+        res[name] = (dq, dk)
+    assert torch.equal(res["proj"][0], unperm(res["heads"][0])) and float(res["proj"][0][1].abs().max()) > 0
+    assert float(res["proj"][0][0].abs().max()) == 0.0
+    assert torch.equal(res["proj"][1], unperm(res["heads"][1])) and float(res["proj"][1][1].abs().max()) > 0
