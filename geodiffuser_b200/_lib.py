@@ -44,8 +44,11 @@ SIGNATURES = {
     "gd_latent_update": [P, P, P, I, F, L, P, P],
     "gd_norm_rescale": [P, L, F, P, P],
     "gd_latent_blend": [P, P, P, I, I, L, P, P],
-    "gd_group_norm_nhwc_fwd": [P, P, P, I, I, I, I, I, F, I, P, L, P, P, P],
-    "gd_group_norm_nhwc_bwd": [P, P, P, P, I, P, I, I, I, I, I, P, L, P, P],
+    "gd_group_norm_nhwc_fwd": [P, P, P, P, I, I, I, I, I, F, I, P, L, P, P, P, P],
+    "gd_group_norm_nhwc_bwd": [P, P, P, P, P, I, P, I, I, I, I, I, P, L, P, P, P],
+    "gd_geglu_fwd": [P, L, I, P, P],
+    "gd_geglu_bwd": [P, P, L, I, P, P],
+    "gd_add_bias_residual": [P, P, P, L, I, P, P],
     "gd_group_norm_nhwc_workspace": [I, I, I, I],
 }
 

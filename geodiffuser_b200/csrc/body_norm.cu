@@ -21,11 +21,14 @@ typedef __nv_bfloat16 bf16;
 struct GnParams {
     const bf16* x;        // (B, HW, C)
     const bf16* dy;       // backward only
+    const bf16* pre_bias; // optional (B, C): the normalised tensor is x + pre_bias[b, c] (conv bias + time-embedding shift folded in)
     const void* gamma;    // (C) bf16 or fp32
     const void* beta;     // (C)
     int w_bf16;
     float* partial;       // (B, n_chunks, G, 2)
     float* stats;         // (B, G, 2) mean, rstd : written by the forward, read by the backward
+    float* red;           // (B, G, 2) backward only: mean_g(t), mean_g(t * x_hat)
+    unsigned* counter;    // (B) zero on entry, zero again on exit: the last chunk of a batch entry finishes that entry's reduction
     bf16* out;            // y or dx (B, HW, C)
     int B, HW, C, G, Cg, n_chunks, rows_per_chunk, nslot, rpi;
     float eps;
@@ -60,7 +63,10 @@ __global__ void __launch_bounds__(320) gn_partial_kernel(const GnParams p) {
     for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
     if (active) {
         const int row0 = chunk * p.rows_per_chunk, row1 = min(p.HW, row0 + p.rows_per_chunk);
-        float mean[8], rstd[8], ga[8], be[8];
+        float mean[8], rstd[8], ga[8], be[8], pb[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pb[j] = 0.f;
+        if (p.pre_bias) unpack8(*reinterpret_cast<const uint4*>(p.pre_bias + (long)b * C + c0), pb);
         if (BWD) {
             int g = c0 / Cg;
 #pragma unroll
@@ -76,6 +82,8 @@ __global__ void __launch_bounds__(320) gn_partial_kernel(const GnParams p) {
             const long off = ((long)b * p.HW + row) * C + c0;
             float f[8];
             unpack8(*reinterpret_cast<const uint4*>(p.x + off), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += pb[j];
             if (!BWD) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { a1[j] += f[j]; a2[j] += f[j] * f[j]; }
@@ -112,23 +120,35 @@ __global__ void __launch_bounds__(320) gn_partial_kernel(const GnParams p) {
         if (j == 0) {
             float* dst = p.partial + (((long)b * p.n_chunks + chunk) * p.G + g) * 2;
             dst[0] = s1; dst[1] = s2;
+            __threadfence();
         }
     }
-}
-
-template <int BWD>
-__global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
-    __shared__ float st[32][4];     // forward: mean, rstd ; backward: mean, rstd, m1, m2
-    const int t = threadIdx.x, b = blockIdx.y;
-    const int C = p.C, Cg = p.Cg, nslot = p.nslot;
+    // the chunk that finishes last adds the partial sums of its batch entry -- in chunk order, whichever chunk it is, so the result does not
+    // depend on the arrival order -- and publishes the group statistics; the apply kernel then starts without a reduction prologue
+    __shared__ int is_last;
+    __syncthreads();
+    if (t == 0) is_last = (atomicAdd(p.counter + b, 1u) == (unsigned)(p.n_chunks - 1));
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
     if (t < p.G * 8) {
         const unsigned lanes = __activemask();
         const int g = t >> 3, j = t & 7;
-        float s1 = 0.f, s2 = 0.f;
-        for (int k = j; k < p.n_chunks; k += 8) {
-            const float* src = p.partial + (((long)b * p.n_chunks + k) * p.G + g) * 2;
-            s1 += src[0]; s2 += src[1];
+        float u1[4] = {0.f, 0.f, 0.f, 0.f}, u2[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* src = p.partial + ((long)b * p.n_chunks * p.G + g) * 2;
+        int k = j;
+        for (; k + 24 < p.n_chunks; k += 32) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float2 v = __ldcg(reinterpret_cast<const float2*>(src + (long)(k + 8 * u) * p.G * 2));
+                u1[u] += v.x; u2[u] += v.y;
+            }
         }
+        for (int u = 0; k < p.n_chunks; k += 8, ++u) {
+            const float2 v = __ldcg(reinterpret_cast<const float2*>(src + (long)k * p.G * 2));
+            u1[u & 3] += v.x; u2[u & 3] += v.y;
+        }
+        float s1 = (u1[0] + u1[1]) + (u1[2] + u1[3]), s2 = (u2[0] + u2[1]) + (u2[2] + u2[3]);
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) { s1 += __shfl_xor_sync(lanes, s1, o); s2 += __shfl_xor_sync(lanes, s2, o); }
         if (j == 0) {
@@ -136,14 +156,25 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
             if (!BWD) {
                 const float mean = s1 * inv_n;
                 const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
-                const float rstd = rsqrtf(var + p.eps);
-                st[g][0] = mean; st[g][1] = rstd;
-                if (blockIdx.x == 0 && p.stats) { p.stats[((long)b * p.G + g) * 2] = mean; p.stats[((long)b * p.G + g) * 2 + 1] = rstd; }
+                p.stats[((long)b * p.G + g) * 2] = mean;
+                p.stats[((long)b * p.G + g) * 2 + 1] = rsqrtf(var + p.eps);
             } else {
-                st[g][0] = p.stats[((long)b * p.G + g) * 2]; st[g][1] = p.stats[((long)b * p.G + g) * 2 + 1];
-                st[g][2] = s1 * inv_n; st[g][3] = s2 * inv_n;
+                p.red[((long)b * p.G + g) * 2] = s1 * inv_n;
+                p.red[((long)b * p.G + g) * 2 + 1] = s2 * inv_n;
             }
         }
+    }
+    if (t == 0) p.counter[b] = 0u;
+}
+
+template <int BWD>
+__global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
+    __shared__ float st[32][4];     // forward: mean, rstd ; backward: mean, rstd, m1, m2
+    const int t = threadIdx.x, b = blockIdx.y;
+    const int C = p.C, Cg = p.Cg, nslot = p.nslot;
+    if (t < p.G) {
+        st[t][0] = p.stats[((long)b * p.G + t) * 2]; st[t][1] = p.stats[((long)b * p.G + t) * 2 + 1];
+        if (BWD) { st[t][2] = p.red[((long)b * p.G + t) * 2]; st[t][3] = p.red[((long)b * p.G + t) * 2 + 1]; }
     }
     __syncthreads();
     const long nvec = (long)p.HW * nslot;
@@ -154,14 +185,27 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
         float f[8], d[8];
         unpack8(*reinterpret_cast<const uint4*>(p.x + off), f);
         if (BWD) unpack8(*reinterpret_cast<const uint4*>(p.dy + off), d);
+        if (p.pre_bias) {
+            float pb[8];
+            unpack8(*reinterpret_cast<const uint4*>(p.pre_bias + (long)b * C + c0), pb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] += pb[j];
+        }
         int g = c0 / Cg;
         uint4 o;
         __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
-        float r[8];
+        float r[8], gav[8], bev[8];
+        if (p.w_bf16) {
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gamma) + c0), gav);
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.beta) + c0), bev);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { gav[j] = reinterpret_cast<const float*>(p.gamma)[c0 + j]; bev[j] = reinterpret_cast<const float*>(p.beta)[c0 + j]; }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             while (c0 + j >= (g + 1) * Cg) ++g;
-            const float ga = ldw(p.gamma, p.w_bf16, c0 + j), be = ldw(p.beta, p.w_bf16, c0 + j);
+            const float ga = gav[j], be = bev[j];
             const float xh = (f[j] - st[g][0]) * st[g][1];
             if (!BWD) {
                 float z = xh * ga + be;
@@ -179,6 +223,64 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
     }
 }
 
+// ---- GEGLU: out = a * gelu(g) for proj = [a | g] (rows of 2F, exact erf GELU as F.gelu), and its gradient --------------------------
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+    return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ uint4 pack8(const float* r) {
+    uint4 o;
+    __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(r[2 * j], r[2 * j + 1]);
+    return o;
+}
+
+__global__ void geglu_fwd_kernel(const bf16* __restrict__ proj, long rows, int F, bf16* __restrict__ out) {
+    const int vpr = F >> 3;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * vpr) return;
+    const long r = i / vpr;
+    const int c = (int)(i - r * vpr) << 3;
+    float a[8], g[8];
+    unpack8(*reinterpret_cast<const uint4*>(proj + r * 2 * F + c), a);
+    unpack8(*reinterpret_cast<const uint4*>(proj + r * 2 * F + F + c), g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= gelu_f(g[j]);
+    *reinterpret_cast<uint4*>(out + r * F + c) = pack8(a);
+}
+
+__global__ void geglu_bwd_kernel(const bf16* __restrict__ proj, const bf16* __restrict__ dy, long rows, int F, bf16* __restrict__ dproj) {
+    const int vpr = F >> 3;
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * vpr) return;
+    const long r = i / vpr;
+    const int c = (int)(i - r * vpr) << 3;
+    float a[8], g[8], d[8], da[8], dg[8];
+    unpack8(*reinterpret_cast<const uint4*>(proj + r * 2 * F + c), a);
+    unpack8(*reinterpret_cast<const uint4*>(proj + r * 2 * F + F + c), g);
+    unpack8(*reinterpret_cast<const uint4*>(dy + r * F + c), d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { da[j] = d[j] * gelu_f(g[j]); dg[j] = d[j] * a[j] * gelu_grad_f(g[j]); }
+    *reinterpret_cast<uint4*>(dproj + r * 2 * F + c) = pack8(da);
+    *reinterpret_cast<uint4*>(dproj + r * 2 * F + F + c) = pack8(dg);
+}
+
+// out = a + b + bias[c] over (rows, C) bf16 (a residual add with the producing convolution's bias folded in)
+__global__ void add_bias_residual_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, const bf16* __restrict__ bias, long nvec, int C,
+                                         bf16* __restrict__ out) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nvec) return;
+    const int c = (int)((i << 3) % C);
+    float x[8], y[8], z[8];
+    unpack8(*reinterpret_cast<const uint4*>(a + (i << 3)), x);
+    unpack8(*reinterpret_cast<const uint4*>(b + (i << 3)), y);
+    unpack8(*reinterpret_cast<const uint4*>(bias + c), z);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = (x[j] + y[j]) + z[j];
+    *reinterpret_cast<uint4*>(out + (i << 3)) = pack8(x);
+}
+
 static int gn_plan(GnParams& p, long ws_floats) {
     p.Cg = p.C / p.G;
     p.nslot = p.C / 8;
@@ -190,8 +292,9 @@ static int gn_plan(GnParams& p, long ws_floats) {
     if (n_chunks > max_chunks) n_chunks = max_chunks;
     p.rows_per_chunk = (p.HW + n_chunks - 1) / n_chunks;
     p.n_chunks = (p.HW + p.rows_per_chunk - 1) / p.rows_per_chunk;
-    if ((long)p.B * p.n_chunks * p.G * 2 > ws_floats)
-        return set_error(GD_ERR_INVALID, "group norm: workspace of %ld floats < %ld", ws_floats, (long)p.B * p.n_chunks * p.G * 2);
+    const long need = (long)p.B * p.n_chunks * p.G * 2 + (long)p.B * p.G * 2;
+    if (need > ws_floats) return set_error(GD_ERR_INVALID, "group norm: workspace of %ld floats < %ld", ws_floats, need);
+    p.red = p.partial + (long)p.B * p.n_chunks * p.G * 2;
     return GD_OK;
 }
 
@@ -219,34 +322,59 @@ using namespace gd;
 
 extern "C" {
 
-// y = silu?(group_norm(x)) for x (B, HW, C) bf16 channels-last; gamma / beta (C) bf16 (w_is_bf16 = 1) or fp32.  stats (B, G, 2) receives
-// (mean, rstd) for the backward (may be NULL).  workspace: >= gd_group_norm_nhwc_workspace(B, HW, C, G) floats.
-int gd_group_norm_nhwc_fwd(const void* x, const void* gamma, const void* beta, int w_is_bf16, int B, int HW, int C, int G, float eps, int silu,
-                           float* workspace, long workspace_floats, float* stats, void* y, void* stream) {
-    GD_CHECK_ARG(x && gamma && beta && workspace && y && B > 0 && HW > 0 && C > 0 && G > 0 && G <= 32);
+// y = silu?(group_norm(x + pre_bias[b, c])) for x (B, HW, C) bf16 channels-last (pre_bias (B, C) bf16 or NULL); gamma / beta (C) bf16 (w_is_bf16 = 1) or fp32.  stats (B, G, 2) receives
+// (mean, rstd) (also the backward's input).  workspace: >= gd_group_norm_nhwc_workspace(B, HW, C, G) floats.  counters: >= B unsigned ints
+// that are ZERO on entry (they are zero again on exit: allocate and clear once, reuse for every call on the same stream).
+int gd_group_norm_nhwc_fwd(const void* x, const void* pre_bias, const void* gamma, const void* beta, int w_is_bf16, int B, int HW, int C, int G, float eps, int silu,
+                           float* workspace, long workspace_floats, unsigned* counters, float* stats, void* y, void* stream) {
+    GD_CHECK_ARG(x && gamma && beta && workspace && counters && stats && y && B > 0 && HW > 0 && C > 0 && G > 0 && G <= 32);
     if (C % 8 != 0 || C % G != 0) return set_error(GD_ERR_UNSUPPORTED, "group norm: C = %d must be a multiple of 8 and of G = %d", C, G);
     GnParams p;
-    p.x = (const bf16*)x; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.w_bf16 = w_is_bf16; p.partial = workspace; p.stats = stats;
-    p.out = (bf16*)y; p.B = B; p.HW = HW; p.C = C; p.G = G; p.eps = eps; p.silu = silu;
+    p.x = (const bf16*)x; p.pre_bias = (const bf16*)pre_bias; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.w_bf16 = w_is_bf16; p.partial = workspace; p.stats = stats;
+    p.counter = counters; p.out = (bf16*)y; p.B = B; p.HW = HW; p.C = C; p.G = G; p.eps = eps; p.silu = silu;
     return gn_run<0>(p, workspace_floats, (cudaStream_t)stream);
 }
 
 // dx of the above given dy (B, HW, C) bf16 and the forward's stats; gradients of gamma / beta are not produced (the body's weights
 // are frozen in the edit loop: optimization.py:213-219 differentiates w.r.t. the latent and the context only).
-int gd_group_norm_nhwc_bwd(const void* x, const void* dy, const void* gamma, const void* beta, int w_is_bf16, const float* stats, int B, int HW,
-                           int C, int G, int silu, float* workspace, long workspace_floats, void* dx, void* stream) {
-    GD_CHECK_ARG(x && dy && gamma && beta && stats && workspace && dx && B > 0 && HW > 0 && C > 0 && G > 0 && G <= 32);
+int gd_group_norm_nhwc_bwd(const void* x, const void* pre_bias, const void* dy, const void* gamma, const void* beta, int w_is_bf16, const float* stats, int B, int HW,
+                           int C, int G, int silu, float* workspace, long workspace_floats, unsigned* counters, void* dx, void* stream) {
+    GD_CHECK_ARG(x && dy && gamma && beta && stats && workspace && counters && dx && B > 0 && HW > 0 && C > 0 && G > 0 && G <= 32);
     if (C % 8 != 0 || C % G != 0) return set_error(GD_ERR_UNSUPPORTED, "group norm: C = %d must be a multiple of 8 and of G = %d", C, G);
     GnParams p;
-    p.x = (const bf16*)x; p.dy = (const bf16*)dy; p.gamma = gamma; p.beta = beta; p.w_bf16 = w_is_bf16; p.partial = workspace;
-    p.stats = const_cast<float*>(stats); p.out = (bf16*)dx; p.B = B; p.HW = HW; p.C = C; p.G = G; p.eps = 0.f; p.silu = silu;
+    p.x = (const bf16*)x; p.pre_bias = (const bf16*)pre_bias; p.dy = (const bf16*)dy; p.gamma = gamma; p.beta = beta; p.w_bf16 = w_is_bf16; p.partial = workspace;
+    p.stats = const_cast<float*>(stats); p.counter = counters; p.out = (bf16*)dx; p.B = B; p.HW = HW; p.C = C; p.G = G; p.eps = 0.f; p.silu = silu;
     return gn_run<1>(p, workspace_floats, (cudaStream_t)stream);
 }
 
 // floats of workspace the two entry points above need (an upper bound that does not depend on the plan's details)
 int gd_group_norm_nhwc_workspace(int B, int HW, int C, int G) {
     (void)HW; (void)C;
-    return (2 * 148 + B) * G * 2;
+    return (2 * 148 + B) * G * 2 + B * G * 2;
+}
+
+// GEGLU of the feed-forward blocks: out (rows, F) = proj[:, :F] * gelu(proj[:, F:]) for proj (rows, 2F) bf16, F % 8 == 0 (torch: chunk + gelu +
+// mul on strided halves = 2 non-vectorised kernels), and dproj given dy.
+int gd_geglu_fwd(const void* proj, long rows, int F, void* out, void* stream) {
+    GD_CHECK_ARG(proj && out && rows > 0 && F > 0 && (F % 8) == 0);
+    geglu_fwd_kernel<<<ceil_div(rows * (F / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)proj, rows, F, (bf16*)out);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+int gd_geglu_bwd(const void* proj, const void* dy, long rows, int F, void* dproj, void* stream) {
+    GD_CHECK_ARG(proj && dy && dproj && rows > 0 && F > 0 && (F % 8) == 0);
+    geglu_bwd_kernel<<<ceil_div(rows * (F / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)proj, (const bf16*)dy, rows, F, (bf16*)dproj);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
+// out = a + b + bias[c] for a, b, out (rows, C) bf16 channels-last, bias (C) bf16, C % 8 == 0
+int gd_add_bias_residual(const void* a, const void* b, const void* bias, long rows, int C, void* out, void* stream) {
+    GD_CHECK_ARG(a && b && bias && out && rows > 0 && C > 0 && (C % 8) == 0);
+    const long nvec = rows * (C / 8);
+    add_bias_residual_kernel<<<ceil_div(nvec, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (const bf16*)bias, nvec, C, (bf16*)out);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
 }
 
 }  // extern "C"

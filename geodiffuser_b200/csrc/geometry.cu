@@ -282,58 +282,108 @@ __global__ void splat_composite_kernel(const TIn* __restrict__ src, long sb, lon
     stf<TOut>(out + (long)b * ob + (long)p * op + (long)c * oc, w);
 }
 
-// Row form of the composite for channel-fastest sources sharing one index (the per-layer query warp: src (B=heads, P, C=head_dim), Bi = 1):
-// one warp per output pixel.  The K blend weights cum_k * alpha_k depend only on the pixel, so they are formed once per warp -- same IEEE
-// operations in the same order as splat_composite_kernel, hence bit-identical results -- instead of once per (head, channel); the lanes
-// then sweep the B*C feature values of that pixel (rows of C contiguous elements per head -> coalesced gathers).
+// Row form of the composite for channel-fastest sources sharing one index (the per-layer query warp: src (B=heads, P, C=head_dim), Bi = 1).
+// A block takes PPB output pixels.  Phase 1: the K blend weights cum_k * alpha_k of each pixel -- they depend only on the pixel -- are formed
+// once (same IEEE operations in the same order as splat_composite_kernel, so results are bit-identical) instead of once per (head, channel).
+// Phase 2: one thread per (pixel, head, 8-channel vector): K independent 16-byte gathers, explicit mul / add (no contraction).
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float* f);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float* f) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float* f) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 t = __bfloat1622float2(h[j]); f[2 * j] = t.x; f[2 * j + 1] = t.y; }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float* f);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float* f) {
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    *reinterpret_cast<uint4*>(p) = v;
+}
+
+constexpr int ROWS_MAXPPB = 8, ROWS_MAXK = 32;
+
 template <typename TIn, typename TOut>
-__global__ void splat_composite_rows_kernel(const TIn* __restrict__ src, long sb, long sp, const int* __restrict__ idx,
-                                            const float* __restrict__ dist2, int B, int P, int C, int K, float r2, float tau,
-                                            const float* __restrict__ blend, int post, TOut* __restrict__ out, long ob, long op) {
-    const int lane = threadIdx.x & 31;
-    const int p = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (p >= P) return;
-    int n = -1;
-    float a = 0.0f;
-    if (lane < K) {
-        n = idx[(long)p * K + lane];
-        if (n >= 0) {
-            a = __fsub_rn(1.0f, __fsqrt_rn(fminf(fmaxf(__fdiv_rn(dist2[(long)p * K + lane], r2), 1e-3f), 1.0f)));
-            if (tau != 1.0f) a = powf(a, tau);
+__global__ void __launch_bounds__(128) splat_composite_rows_kernel(const TIn* __restrict__ src, long sb, long sp, const int* __restrict__ idx,
+                                                                   const float* __restrict__ dist2, int B, int P, int C, int K, float r2,
+                                                                   float tau, const float* __restrict__ blend, int post, TOut* __restrict__ out,
+                                                                   long ob, long op, int ppb) {
+    __shared__ float s_w[ROWS_MAXPPB][ROWS_MAXK];
+    __shared__ int s_n[ROWS_MAXPPB][ROWS_MAXK];
+    __shared__ int s_cnt[ROWS_MAXPPB];
+    const int p0 = blockIdx.x * ppb;
+    // phase 1a: alpha of every (pixel, slot)
+    for (int i = threadIdx.x; i < ppb * K; i += blockDim.x) {
+        const int pl = i / K, k = i - pl * K, p = p0 + pl;
+        int n = -1;
+        float a = 0.0f;
+        if (p < P) {
+            n = idx[(long)p * K + k];
+            if (n >= 0) {
+                a = __fsub_rn(1.0f, __fsqrt_rn(fminf(fmaxf(__fdiv_rn(dist2[(long)p * K + k], r2), 1e-3f), 1.0f)));   // warp_utils.py:131-140
+                if (tau != 1.0f) a = powf(a, tau);
+            }
         }
+        s_w[pl][k] = a;
+        s_n[pl][k] = n;
     }
-    // weights in slot order; empty slots (n < 0) are skipped by the reference loop: weight 0 is NOT the same as skipping only for the
-    // accumulate of a -0.0 / NaN product, so keep the skip by compacting valid slots to the front
-    const unsigned valid = __ballot_sync(0xffffffffu, n >= 0);
-    float cum = 1.0f, w_mine = 0.0f;
-    int n_mine = -1, cnt = 0;
-    for (int k = 0; k < K; ++k) {
-        const float ak = __shfl_sync(0xffffffffu, a, k);
-        const int nk = __shfl_sync(0xffffffffu, n, k);
-        if (!((valid >> k) & 1u)) continue;
-        const float wk = __fmul_rn(cum, ak);
-        cum = __fmul_rn(cum, __fsub_rn(1.0f, ak));
-        if (lane == cnt) { w_mine = wk; n_mine = nk; }
-        ++cnt;
+    __syncthreads();
+    // phase 1b: front-to-back weights, empty slots (n < 0) skipped as in the reference loop -> valid slots compacted to the front
+    if (threadIdx.x < ppb) {
+        const int pl = threadIdx.x;
+        float cum = 1.0f;
+        int cnt = 0;
+        for (int k = 0; k < K; ++k) {
+            const int n = s_n[pl][k];
+            if (n < 0) continue;
+            const float a = s_w[pl][k];
+            s_w[pl][cnt] = __fmul_rn(cum, a);
+            s_n[pl][cnt] = n;
+            cum = __fmul_rn(cum, __fsub_rn(1.0f, a));
+            ++cnt;
+        }
+        s_cnt[pl] = cnt;
     }
-    const float m = blend ? blend[p] : 0.0f;
-    const int total = B * C;
-    for (int e0 = 0; e0 < total; e0 += 32) {      // uniform trip count: every lane takes part in the shuffles
-        const int e = e0 + lane;
-        const bool on = e < total;
-        const int b = on ? e / C : 0, c = on ? e - b * C : 0;
+    __syncthreads();
+    // phase 2
+    const int vpr = C >> 3;                 // 8-channel vectors per (pixel, head) row
+    const int per_pixel = B * vpr;
+    for (int t = threadIdx.x; t < ppb * per_pixel; t += blockDim.x) {
+        const int pl = t / per_pixel, r = t - pl * per_pixel, p = p0 + pl;
+        if (p >= P) continue;
+        const int b = r / vpr, c = (r - b * vpr) << 3;
         const TIn* s = src + (long)b * sb + c;
-        float acc = 0.0f;
+        const int cnt = s_cnt[pl];
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
         for (int k = 0; k < cnt; ++k) {
-            const float wk = __shfl_sync(0xffffffffu, w_mine, k);
-            const int nk = __shfl_sync(0xffffffffu, n_mine, k);
-            acc = __fadd_rn(acc, __fmul_rn(wk, ldf<TIn>(s + (long)nk * sp)));
+            float f[8];
+            ld8<TIn>(s + (long)s_n[pl][k] * sp, f);
+            const float wk = s_w[pl][k];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(wk, f[j]));
         }
-        if (!on) continue;
-        float w = __half2float(__float2half_rn(acc));
-        if (blend) w = __fadd_rn(__fmul_rn(ldf<TIn>(s + (long)p * sp), __fsub_rn(1.0f, m)), __fmul_rn(m, w));
-        if (post == 1) w = bin05(w);
-        stf<TOut>(out + (long)b * ob + (long)p * op + c, w);
+        float q[8];
+        const float m = blend ? blend[p] : 0.0f;
+        if (blend) ld8<TIn>(s + (long)p * sp, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float w = __half2float(__float2half_rn(acc[j]));   // .to(torch.half)  warp_utils.py:176
+            if (blend) w = __fadd_rn(__fmul_rn(q[j], __fsub_rn(1.0f, m)), __fmul_rn(m, w));
+            if (post == 1) w = bin05(w);
+            acc[j] = w;
+        }
+        st8<TOut>(out + (long)b * ob + (long)p * op + c, acc);
     }
 }
 
@@ -488,10 +538,11 @@ int gd_splat_composite(const void* src, int src_dtype, int layout, const int* id
     const long total = (long)B * P * C;
     const long sb = (long)P * C, sp = layout ? C : 1, sc = layout ? 1 : P;
     cudaStream_t st = (cudaStream_t)stream;
-    if (layout == 1 && Bi == 1 && K <= 32 && (long)B * C >= 32) {   // per-layer query warp: one warp per pixel, weights formed once
-        const int gr = ceil_div((long)P * 32, 256);
+    if (layout == 1 && Bi == 1 && K <= ROWS_MAXK && (C % 8) == 0) {   // per-layer query warp: blend weights formed once per pixel
+        const int ppb = P >= 2048 ? 8 : 2;
+        const int gr = ceil_div(P, ppb);
 #define GD_LAUNCH_ROWS(TI, TO) \
-    splat_composite_rows_kernel<TI, TO><<<gr, 256, 0, st>>>((const TI*)src, sb, sp, idx, dist2, B, P, C, K, r2, tau, blend_mask, post, (TO*)out, sb, sp)
+    splat_composite_rows_kernel<TI, TO><<<gr, 128, 0, st>>>((const TI*)src, sb, sp, idx, dist2, B, P, C, K, r2, tau, blend_mask, post, (TO*)out, sb, sp, ppb)
         if (src_dtype == 0 && out_dtype == 0) GD_LAUNCH_ROWS(float, float);
         else if (src_dtype == 0 && out_dtype == 1) GD_LAUNCH_ROWS(float, __nv_bfloat16);
         else if (src_dtype == 1 && out_dtype == 0) GD_LAUNCH_ROWS(__nv_bfloat16, float);
@@ -519,14 +570,16 @@ int gd_splat_composite(const void* src, int src_dtype, int layout, const int* id
 int gd_splat_composite_rows(const void* src, int src_dtype, const long* src_strides, const int* idx, const float* dist2, int B, int P, int C,
                             int K, float r2, float tau, const float* blend_mask, int post, void* out, int out_dtype, const long* out_strides,
                             void* stream) {
-    GD_CHECK_ARG(src && idx && dist2 && out && B > 0 && P > 0 && C > 0 && K > 0 && K <= 32);
+    GD_CHECK_ARG(src && idx && dist2 && out && B > 0 && P > 0 && C > 0 && (C % 8) == 0 && K > 0 && K <= ROWS_MAXK);
     GD_CHECK_ARG((src_dtype == 0 || src_dtype == 1) && (out_dtype == 0 || out_dtype == 1));
     const long sp = src_strides ? src_strides[0] : C, sb = src_strides ? src_strides[1] : (long)P * C;
     const long op = out_strides ? out_strides[0] : C, ob = out_strides ? out_strides[1] : (long)P * C;
+    GD_CHECK_ARG((sp % 8) == 0 && (sb % 8) == 0 && (op % 8) == 0 && (ob % 8) == 0);
     cudaStream_t st = (cudaStream_t)stream;
-    const int gr = ceil_div((long)P * 32, 256);
+    const int ppb = P >= 2048 ? 8 : 2;
+    const int gr = ceil_div(P, ppb);
 #define GD_LAUNCH_ROWS(TI, TO) \
-    splat_composite_rows_kernel<TI, TO><<<gr, 256, 0, st>>>((const TI*)src, sb, sp, idx, dist2, B, P, C, K, r2, tau, blend_mask, post, (TO*)out, ob, op)
+    splat_composite_rows_kernel<TI, TO><<<gr, 128, 0, st>>>((const TI*)src, sb, sp, idx, dist2, B, P, C, K, r2, tau, blend_mask, post, (TO*)out, ob, op, ppb)
     if (src_dtype == 0 && out_dtype == 0) GD_LAUNCH_ROWS(float, float);
     else if (src_dtype == 0 && out_dtype == 1) GD_LAUNCH_ROWS(float, __nv_bfloat16);
     else if (src_dtype == 1 && out_dtype == 0) GD_LAUNCH_ROWS(__nv_bfloat16, float);

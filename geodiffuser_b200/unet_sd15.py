@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 import os
 
-from .body_ops import group_norm_act
+from .body_ops import add_bias_residual, conv1x1, fast_body, geglu, group_norm_act
 
 BODY_CHANNELS_LAST = os.environ.get("GD_BODY_NCHW", "0") != "1"   # bf16 body layout: NHWC (cuDNN's native tensor-core layout) unless overridden
 
@@ -73,8 +73,7 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward(self, x):
-        x, gate = self.proj(x).chunk(2, dim=-1)
-        return x * F.gelu(gate)
+        return geglu(self.proj(x))
 
 
 class FeedForward(nn.Module):
@@ -115,12 +114,12 @@ class Transformer2DModel(nn.Module):
     def forward(self, x, context):
         b, c, h, w = x.shape
         res = x
-        x = self.proj_in(group_norm_act(self.norm, x))
+        x = conv1x1(self.proj_in, group_norm_act(self.norm, x))
         x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
         for blk in self.transformer_blocks:
             x = blk(x, context)
         x = x.reshape(b, h, w, c).permute(0, 3, 1, 2)
-        return self.proj_out(x) + res
+        return conv1x1(self.proj_out, x) + res
 
 
 class ResnetBlock2D(nn.Module):
@@ -133,7 +132,23 @@ class ResnetBlock2D(nn.Module):
         self.conv2 = nn.Conv2d(cout, cout, 3, padding=1)
         self.conv_shortcut = nn.Conv2d(cin, cout, 1) if cin != cout else None
 
+    def _shift_bias(self):
+        # conv1.bias + time_emb_proj.bias: one (C) vector, so that the per-sample shift below is a single GEMM with a bias epilogue
+        b = self.__dict__.get("_tb")
+        if b is None or b.device != self.conv1.bias.device or b.dtype != self.conv1.bias.dtype:
+            b = self.__dict__["_tb"] = (self.conv1.bias.detach().float() + self.time_emb_proj.bias.detach().float()).to(self.conv1.bias.dtype)
+        return b
+
     def forward(self, x, temb):
+        if fast_body(x) and not self.conv1.bias.requires_grad:
+            # product setting (bf16, channels-last, frozen weights): conv1's bias and the time-embedding shift are folded into norm2
+            # (one (B, C) vector added while the norm reads its input), conv2's bias into the residual add
+            h = F.conv2d(group_norm_act(self.norm1, x, silu=True), self.conv1.weight, None, padding=1)
+            shift = F.linear(F.silu(temb), self.time_emb_proj.weight, self._shift_bias())
+            h = F.conv2d(group_norm_act(self.norm2, h, silu=True, pre_bias=shift), self.conv2.weight, None, padding=1)
+            if self.conv_shortcut is not None:
+                x = conv1x1(self.conv_shortcut, x)
+            return add_bias_residual(x, h, self.conv2.bias)
         h = self.conv1(group_norm_act(self.norm1, x, silu=True))
         h = h + self.time_emb_proj(F.silu(temb))[:, :, None, None]
         h = self.conv2(group_norm_act(self.norm2, h, silu=True))

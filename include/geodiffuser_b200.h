@@ -181,12 +181,22 @@ int gd_latent_blend(const float* a, const float* b, const float* mask, int hw, i
  * GroupNorm (+ SiLU) on channels-last bf16 activations: torch's CUDA group_norm round-trips through NCHW (2 layout copies + 4 kernels
  * per norm, 61 norms per UNet evaluation), which hides the path behind the body.  x, y, dy, dx (B, HW, C) bf16, C % 8 == 0, G <= 32;
  * gamma / beta (C) bf16 or fp32; stats (B, G, 2) = (mean, rstd) saved for the backward; workspace >= gd_group_norm_nhwc_workspace()
- * floats.  The backward returns dx only (the body's weights are frozen in the edit loop, optimization.py:213-219). */
-int gd_group_norm_nhwc_fwd(const void* x, const void* gamma, const void* beta, int w_is_bf16, int B, int HW, int C, int G, float eps, int silu,
-                           float* workspace, long workspace_floats, float* stats, void* y, void* stream);
-int gd_group_norm_nhwc_bwd(const void* x, const void* dy, const void* gamma, const void* beta, int w_is_bf16, const float* stats, int B, int HW,
-                           int C, int G, int silu, float* workspace, long workspace_floats, void* dx, void* stream);
+ * floats; counters: >= B unsigned ints, zero on entry and zero again on exit (clear once, reuse on the same stream).  The backward returns dx only (the body's weights are frozen in the edit loop, optimization.py:213-219). */
+int gd_group_norm_nhwc_fwd(const void* x, const void* pre_bias, const void* gamma, const void* beta, int w_is_bf16, int B, int HW, int C, int G, float eps, int silu,
+                           float* workspace, long workspace_floats, unsigned* counters, float* stats, void* y, void* stream);
+int gd_group_norm_nhwc_bwd(const void* x, const void* pre_bias, const void* dy, const void* gamma, const void* beta, int w_is_bf16, const float* stats, int B, int HW,
+                           int C, int G, int silu, float* workspace, long workspace_floats, unsigned* counters, void* dx, void* stream);
 int gd_group_norm_nhwc_workspace(int B, int HW, int C, int G);
+/* (pre_bias (B, C) bf16 or NULL: the tensor that is normalised is x + pre_bias[b, c] -- the producing convolution's bias and the
+ * time-embedding shift of a ResNet block folded into the norm, instead of two broadcast adds.) */
+
+/* GEGLU of the feed-forward blocks: out (rows, F) = proj[:, :F] * gelu(proj[:, F:]) (exact erf), proj (rows, 2F) bf16, F % 8 == 0; and
+ * dproj (rows, 2F) given dy (rows, F). */
+int gd_geglu_fwd(const void* proj, long rows, int F, void* out, void* stream);
+int gd_geglu_bwd(const void* proj, const void* dy, long rows, int F, void* dproj, void* stream);
+
+/* out = a + b + bias[c] for (rows, C) bf16 channels-last tensors: a residual add with the producing convolution's bias folded in. */
+int gd_add_bias_residual(const void* a, const void* b, const void* bias, long rows, int C, void* out, void* stream);
 
 #ifdef __cplusplus
 }
