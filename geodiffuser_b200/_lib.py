@@ -46,6 +46,7 @@ SIGNATURES = {
     "gd_latent_blend": [P, P, P, I, I, L, P, P],
     "gd_group_norm_nhwc_fwd": [P, P, P, P, I, I, I, I, I, F, I, P, L, P, P, P, P],
     "gd_group_norm_nhwc_bwd": [P, P, P, P, P, I, P, I, I, I, I, I, P, L, P, P, P],
+    "gd_masked_histogram_match": [P, P, P, P, L, I, P, P, P, P],
     "gd_geglu_fwd": [P, L, I, P, P],
     "gd_geglu_bwd": [P, P, L, I, P, P],
     "gd_add_bias_residual": [P, P, P, L, I, P, P],
@@ -56,7 +57,7 @@ _LIB = None
 HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
 LAUNCHES = 0  # CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
 KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2, "gd_attn_bwd_dk_split": 2,
-                    "gd_group_norm_nhwc_fwd": 2, "gd_group_norm_nhwc_bwd": 2, "gd_group_norm_nhwc_workspace": 0}  # every other entry point launches one
+                    "gd_group_norm_nhwc_fwd": 2, "gd_group_norm_nhwc_bwd": 2, "gd_group_norm_nhwc_workspace": 0, "gd_masked_histogram_match": 3}  # every other entry point launches one
 
 
 class GeoDiffuserB200Error(RuntimeError):

@@ -48,9 +48,13 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_fwd_mma_kernel(const AttnFw
     const bf16* Kg = p.k[g] + (long)h * p.kv_hs;
     const bf16* Vg = p.v[g] + (long)h * p.kv_hs;
 
-    // zero everything once so the d..DPAD pad columns (never written by the tile loads) are 0
-    for (int i = tid; i < (5 * 64 * LD) / 8; i += ATT_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
+    // the d..DPAD pad columns are never written by the tile loads but are read by the k-steps: zero them once (head_dim 40 only; the tile
+    // loads touch other addresses, and the first __syncthreads of the key loop orders these stores before any fragment read)
+    if (d < DPAD)
+        for (int i = tid; i < 5 * 64 * ((DPAD - d) / 8); i += ATT_THREADS) {
+            const int r = i / ((DPAD - d) / 8), c = d + (i % ((DPAD - d) / 8)) * 8;
+            *reinterpret_cast<uint4*>(Qs + r * LD + c) = make_uint4(0, 0, 0, 0);
+        }
 
     const int nT = (Nk + 63) / 64;
     load_tile_async<ATT_THREADS>(Qs, LD, Qg, p.q_rs, d, min(64, N - q0), tid);
@@ -207,8 +211,11 @@ __global__ void __launch_bounds__(ATT_THREADS) flash_bwd_mma_kernel(const AttnBw
     const float* lse = p.lse + (long)h * Nq;
     const float* delta = p.delta + (long)h * Nq;
 
-    for (int i = tid; i < (6 * 64 * LD) / 8; i += ATT_THREADS) reinterpret_cast<uint4*>(smem_raw)[i] = make_uint4(0, 0, 0, 0);
-    __syncthreads();
+    if (d < DPAD)       // pad columns d..DPAD (see the forward kernel)
+        for (int i = tid; i < 6 * 64 * ((DPAD - d) / 8); i += ATT_THREADS) {
+            const int r = i / ((DPAD - d) / 8), c = d + (i % ((DPAD - d) / 8)) * 8;
+            *reinterpret_cast<uint4*>(X1 + r * LD + c) = make_uint4(0, 0, 0, 0);
+        }
     // dK walks the queries: with Nk = 77 there are only 2 outer tiles per head, so the query range is split over blockIdx.z
     // (16 CTAs walking 4096 queries serially took 370 us per launch) and the partial sums are added in a fixed order afterwards
     const int nT_all = (ni + 63) / 64;

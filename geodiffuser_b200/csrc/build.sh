@@ -8,8 +8,9 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 COMMON="-O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v $ARCH"
 mkdir -p _obj
 pids=""
-# geometry.cu: bit-exact integer artefacts behind an fp32 pipeline -> no FMA contraction
+# geometry.cu, postprocess.cu: bit-exact artefacts behind a floating-point pipeline -> no FMA contraction
 $NVCC $COMMON -fmad=false -c geometry.cu -o _obj/geometry.o 2> _obj/geometry.log & pids="$pids $!"
+$NVCC $COMMON -fmad=false -c postprocess.cu -o _obj/postprocess.o 2> _obj/postprocess.log & pids="$pids $!"
 for f in attention_mma corr_gemm losses elementwise attention_sm100 body_norm; do
     if [ -f $f.cu ]; then
         $NVCC $COMMON -c $f.cu -o _obj/$f.o 2> _obj/$f.log & pids="$pids $!"

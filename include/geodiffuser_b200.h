@@ -177,6 +177,14 @@ int gd_norm_rescale(float* x, long n, float target_norm, float* norm_out, void* 
 /* editor.py:393-399: out = a (1 - m) + m b, m optionally binarised (> 0.5). */
 int gd_latent_blend(const float* a, const float* b, const float* mask, int hw, int binarize, long n, float* out, void* stream);
 
+/* ---- (5) post-processing ----------------------------------------------------------------------------------- */
+
+/* image_processing.py:24-77 masked_histogram_matching (editor.py:680,683,690): per channel, the source's values are remapped so that its
+ * CDF under mask_source matches the template's CDF under mask.  source, tmpl (npix, C) uint8; masks (npix) float (> 0.5 selects);
+ * counts (C,2,256) int32 and lut (C,256) double: scratch; out (npix, C) double -- the reference's np.interp look-up, bit for bit. */
+int gd_masked_histogram_match(const unsigned char* source, const unsigned char* tmpl, const float* mask, const float* mask_source, long npix,
+                              int C, int* counts, double* lut, double* out, void* stream);
+
 /* ---- caller-side fused op (NOT part of the reference surface; SURVEY 8 row A14 leaves the UNet body to stock torch) -------------
  * GroupNorm (+ SiLU) on channels-last bf16 activations: torch's CUDA group_norm round-trips through NCHW (2 layout copies + 4 kernels
  * per norm, 61 norms per UNet evaluation), which hides the path behind the body.  x, y, dy, dx (B, HW, C) bf16, C % 8 == 0, G <= 32;

@@ -58,3 +58,16 @@ def test_loop_golden_is_pinned_to_reference():
         z = np.load(os.path.join(GOLDEN, f"loop_{kind}_tiny.npz"))
         assert float(z["pin_err_vs_reference"]) <= 1e-2
         assert np.isfinite(z["latents"]).all()
+
+
+def test_postprocess_oracle_vs_reference_golden():
+    """oracle/postprocess_oracle.py (numpy restatement of image_processing.py:24-77) reproduces, bit for bit, the float64 arrays the REAL
+    reference function returned for the seeded inputs (tests/golden/postprocess.npz, made by oracle/make_golden_post.py)"""
+    from oracle import postprocess_oracle as PO
+
+    z = np.load(os.path.join(GOLDEN, "postprocess.npz"))
+    for seed in (1, 2):
+        src, tmpl, mask, mask_source = PO.synthetic_case(seed)
+        out = PO.masked_histogram_matching(src, tmpl, mask, mask_source if bool(z[f"uses_mask_source{seed}"]) else None)
+        assert out.dtype == np.float64
+        np.testing.assert_array_equal(out, z[f"out{seed}"])
