@@ -51,13 +51,14 @@ SIGNATURES = {
     "gd_geglu_bwd": [P, P, L, I, P, P],
     "gd_add_bias_residual": [P, P, P, L, I, P, P],
     "gd_group_norm_nhwc_workspace": [I, I, I, I],
+    "gd_group_norm_config": [I],
 }
 
 _LIB = None
 HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
 LAUNCHES = 0  # CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
 KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2, "gd_attn_bwd_dk_split": 2,
-                    "gd_group_norm_nhwc_fwd": 2, "gd_group_norm_nhwc_bwd": 2, "gd_group_norm_nhwc_workspace": 0, "gd_masked_histogram_match": 3}  # every other entry point launches one
+                    "gd_group_norm_nhwc_fwd": 1, "gd_group_norm_nhwc_bwd": 2, "gd_group_norm_nhwc_workspace": 0, "gd_group_norm_config": 0, "gd_masked_histogram_match": 3}  # every other entry point launches one
 
 
 class GeoDiffuserB200Error(RuntimeError):

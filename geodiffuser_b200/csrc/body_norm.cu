@@ -223,6 +223,160 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const GnParams p) {
     }
 }
 
+// ---- forward in ONE launch: thread-block clusters + distributed shared memory ----------------------------------------------------
+// The two-kernel scheme above pays two launch latencies plus a fence / atomic / re-read chain per norm (~7 us floor each, measured), which
+// dominates at the sizes of the edit loop (0.3 .. 16 MB per tensor).  Here one cluster of 8 CTAs owns a (batch entry, slab of `gs` groups):
+// CTA r stages rows [r*rpc, (r+1)*rpc) x the slab's W channels in shared memory (ONE global read), reduces its per-group partial sums, the
+// cluster exchanges them through DSMEM (rank order: deterministic), and each CTA normalises its staged tile straight out of shared memory.
+constexpr int GNC_CLUSTER = 8;
+constexpr int GNC_THREADS = 512;
+
+struct GnClusterParams {
+    const bf16* x; const bf16* pre_bias; const void* gamma; const void* beta; int w_bf16;
+    float* stats; bf16* out;
+    int B, HW, C, G, Cg, gs, W, nv, rpi, rpc, n_slabs;
+    float eps; int silu;
+};
+
+__global__ void __cluster_dims__(GNC_CLUSTER, 1, 1) __launch_bounds__(GNC_THREADS)
+gn_cluster_fwd_kernel(const GnClusterParams p) {
+    extern __shared__ __align__(16) unsigned char gsm[];
+    __shared__ float part[32][2];      // this CTA's partial (sum, sumsq) per group of the slab
+    __shared__ float st[32][2];        // mean, rstd per group of the slab
+    const int t = threadIdx.x;
+    unsigned rank, cid;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    const int b = cid / p.n_slabs, slab = cid % p.n_slabs;
+    const int W = p.W, nv = p.nv, rpi = p.rpi, Cg = p.Cg, C = p.C;
+    const int c_base = slab * W;
+    const int r0 = rank * p.rpc, r1 = min(p.HW, r0 + p.rpc);
+    const int nact = nv * rpi;                                                   // active threads: (row lane, 8-channel slot)
+    bf16* tile = reinterpret_cast<bf16*>(gsm);                                   // [rpc][W]
+    float* red = reinterpret_cast<float*>(gsm + (size_t)p.rpc * W * 2);          // [16][nact]: k-th accumulator of thread t at red[k*nact + t]
+    float* chs = red + 16 * nact;                                                // [W][2]: per-channel sums of this CTA
+    const bool active = t < nact;
+    const int v = t % nv, rl = t / nv, c0 = v * 8;
+    float pb[8], a1[8], a2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { pb[j] = 0.f; a1[j] = 0.f; a2[j] = 0.f; }
+    if (active) {
+        if (p.pre_bias) unpack8(*reinterpret_cast<const uint4*>(p.pre_bias + (long)b * C + c_base + c0), pb);
+#pragma unroll 4
+        for (int row = r0 + rl; row < r1; row += rpi) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(p.x + ((long)b * p.HW + row) * C + c_base + c0);
+            *reinterpret_cast<uint4*>(tile + (long)(row - r0) * W + c0) = raw;
+            float f[8];
+            unpack8(raw, f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float xv = f[j] + pb[j]; a1[j] += xv; a2[j] += xv * xv; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { red[j * nact + t] = a1[j]; red[(8 + j) * nact + t] = a2[j]; }      // conflict-free: t is the fast index
+    }
+    __syncthreads();
+    // per-channel sums over the row lanes (2W threads, fixed order), then per-group sums (8 threads per group, fixed tree)
+    for (int i = t; i < 2 * W; i += GNC_THREADS) {
+        const int which = i / W, c = i - which * W;
+        const float* src = red + ((which * 8 + (c & 7)) * nact) + (c >> 3);
+        float s = 0.f;
+        for (int rr = 0; rr < rpi; ++rr) s += src[rr * nv];
+        chs[c * 2 + which] = s;
+    }
+    __syncthreads();
+    if (t < p.gs * 8) {
+        const unsigned lanes = __activemask();
+        const int g = t >> 3, j = t & 7;
+        float s1 = 0.f, s2 = 0.f;
+        for (int c = g * Cg + j; c < (g + 1) * Cg; c += 8) { s1 += chs[c * 2]; s2 += chs[c * 2 + 1]; }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) { s1 += __shfl_xor_sync(lanes, s1, o); s2 += __shfl_xor_sync(lanes, s2, o); }
+        if (j == 0) { part[g][0] = s1; part[g][1] = s2; }
+    }
+    // cluster barrier #1: every CTA's `part` is complete and visible cluster-wide
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (t < p.gs) {
+        float s1 = 0.f, s2 = 0.f, u1[GNC_CLUSTER], u2[GNC_CLUSTER];
+        const uint32_t local = (uint32_t)__cvta_generic_to_shared(&part[t][0]);
+#pragma unroll
+        for (int r = 0; r < GNC_CLUSTER; ++r) {        // all 16 remote loads in flight at once (~215 clk each), then summed in rank order
+            uint32_t remote;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(r));
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(u1[r]) : "r"(remote));
+            asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(u2[r]) : "r"(remote + 4));
+        }
+#pragma unroll
+        for (int r = 0; r < GNC_CLUSTER; ++r) { s1 += u1[r]; s2 += u2[r]; }   // rank order: the same sum in every CTA, on every run
+        const float inv_n = 1.0f / ((float)p.HW * (float)Cg);
+        const float mean = s1 * inv_n;
+        const float var = fmaxf(s2 * inv_n - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + p.eps);
+        st[t][0] = mean; st[t][1] = rstd;
+        if (rank == 0 && p.stats) {
+            const int g = slab * p.gs + t;
+            p.stats[((long)b * p.G + g) * 2] = mean; p.stats[((long)b * p.G + g) * 2 + 1] = rstd;
+        }
+    }
+    // cluster barrier #2: nobody leaves (and frees its shared memory) while a sibling may still be reading it
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (!active) return;
+    float ga[8], be[8];
+    if (p.w_bf16) {
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gamma) + c_base + c0), ga);
+        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.beta) + c_base + c0), be);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { ga[j] = reinterpret_cast<const float*>(p.gamma)[c_base + c0 + j]; be[j] = reinterpret_cast<const float*>(p.beta)[c_base + c0 + j]; }
+    }
+    {
+        int g = c0 / Cg;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            while (c0 + j >= (g + 1) * Cg) ++g;
+            // fold everything into y = x * a + c:  a = rstd * gamma,  c = (pre_bias - mean) * a + beta
+            const float a = st[g][1] * ga[j];
+            be[j] = (pb[j] - st[g][0]) * a + be[j];
+            ga[j] = a;
+        }
+    }
+#pragma unroll 4
+    for (int row = r0 + rl; row < r1; row += rpi) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(tile + (long)(row - r0) * W + c0), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float z = f[j] * ga[j] + be[j];
+            if (p.silu) z = __fdividef(z, 1.0f + __expf(-z));
+            f[j] = z;
+        }
+        uint4 o;
+        __nv_bfloat162* oh = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oh[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        *reinterpret_cast<uint4*>(p.out + ((long)b * p.HW + row) * C + c_base + c0) = o;
+    }
+}
+
+// plan of the cluster kernel; false if the shape does not fit (caller falls back to the two-kernel scheme)
+static bool gn_cluster_plan(GnClusterParams& p, size_t* smem) {
+    p.Cg = p.C / p.G;
+    int gs = 0;
+    for (int cand = 1; cand <= p.G; cand *= 2) {
+        if (p.G % cand) break;
+        const int W = cand * p.Cg;
+        if ((W % 8) == 0 && W >= 40) { gs = cand; break; }
+    }
+    if (!gs || gs > 32) return false;
+    p.gs = gs; p.W = gs * p.Cg; p.nv = p.W / 8;
+    if (p.nv > GNC_THREADS) return false;
+    p.rpi = GNC_THREADS / p.nv;
+    p.rpc = (p.HW + GNC_CLUSTER - 1) / GNC_CLUSTER;
+    if (p.rpi > p.rpc) p.rpi = p.rpc;
+    p.n_slabs = p.G / gs;
+    *smem = (size_t)p.rpc * p.W * 2 + ((size_t)16 * p.nv * p.rpi + 2 * p.W) * sizeof(float);
+    return *smem <= 192 * 1024 && (long)p.B * p.n_slabs * GNC_CLUSTER <= 65535L * 8;
+}
+
 // ---- GEGLU: out = a * gelu(g) for proj = [a | g] (rows of 2F, exact erf GELU as F.gelu), and its gradient --------------------------
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
@@ -316,11 +470,19 @@ template <int BWD> static int gn_run(GnParams& p, long ws_floats, cudaStream_t s
     return GD_OK;
 }
 
+static int g_gn_cluster = 1;    // gd_group_norm_config: 1 = one-launch cluster kernel where the shape fits (default), 0 = always two launches
+
 }  // namespace gd
 
 using namespace gd;
 
 extern "C" {
+
+// test / tuning knob (process-wide): selects the forward scheme of gd_group_norm_nhwc_fwd
+int gd_group_norm_config(int use_cluster_kernel) {
+    g_gn_cluster = use_cluster_kernel ? 1 : 0;
+    return GD_OK;
+}
 
 // y = silu?(group_norm(x + pre_bias[b, c])) for x (B, HW, C) bf16 channels-last (pre_bias (B, C) bf16 or NULL); gamma / beta (C) bf16 (w_is_bf16 = 1) or fp32.  stats (B, G, 2) receives
 // (mean, rstd) (also the backward's input).  workspace: >= gd_group_norm_nhwc_workspace(B, HW, C, G) floats.  counters: >= B unsigned ints
@@ -332,6 +494,21 @@ int gd_group_norm_nhwc_fwd(const void* x, const void* pre_bias, const void* gamm
     GnParams p;
     p.x = (const bf16*)x; p.pre_bias = (const bf16*)pre_bias; p.dy = nullptr; p.gamma = gamma; p.beta = beta; p.w_bf16 = w_is_bf16; p.partial = workspace; p.stats = stats;
     p.counter = counters; p.out = (bf16*)y; p.B = B; p.HW = HW; p.C = C; p.G = G; p.eps = eps; p.silu = silu;
+    GnClusterParams c;
+    c.x = p.x; c.pre_bias = p.pre_bias; c.gamma = gamma; c.beta = beta; c.w_bf16 = w_is_bf16; c.stats = stats; c.out = p.out;
+    c.B = B; c.HW = HW; c.C = C; c.G = G; c.eps = eps; c.silu = silu;
+    size_t smem = 0;
+    if (g_gn_cluster && gn_cluster_plan(c, &smem)) {
+        static size_t configured = 0;
+        if (smem > configured) {
+            cudaError_t e = cudaFuncSetAttribute(gn_cluster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(192 * 1024));
+            if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            configured = 192 * 1024;
+        }
+        gn_cluster_fwd_kernel<<<B * c.n_slabs * GNC_CLUSTER, GNC_THREADS, smem, (cudaStream_t)stream>>>(c);
+        GD_CHECK_LAUNCH();
+        return GD_OK;
+    }
     return gn_run<0>(p, workspace_floats, (cudaStream_t)stream);
 }
 

@@ -195,6 +195,9 @@ int gd_group_norm_nhwc_fwd(const void* x, const void* pre_bias, const void* gamm
 int gd_group_norm_nhwc_bwd(const void* x, const void* pre_bias, const void* dy, const void* gamma, const void* beta, int w_is_bf16, const float* stats, int B, int HW,
                            int C, int G, int silu, float* workspace, long workspace_floats, unsigned* counters, void* dx, void* stream);
 int gd_group_norm_nhwc_workspace(int B, int HW, int C, int G);
+/* forward scheme (process-wide knob): 1 = one launch, a cluster of 8 CTAs per (batch entry, slab of groups) staging its rows in shared
+ * memory and exchanging partial sums through distributed shared memory (default where the shape fits); 0 = always the two-launch scheme. */
+int gd_group_norm_config(int use_cluster_kernel);
 /* (pre_bias (B, C) bf16 or NULL: the tensor that is normalised is x + pre_bias[b, c] -- the producing convolution's bias and the
  * time-embedding shift of a ResNet block folded into the norm, instead of two broadcast adds.) */
 

@@ -12,9 +12,19 @@ SHAPES = [(2, 320, 64, 64), (3, 640, 32, 32), (2, 1280, 16, 16), (2, 1280, 8, 8)
           (2, 64, 8, 8), (1, 384, 12, 12), (2, 128, 3, 5)]
 
 
+@pytest.fixture(params=[1, 0], ids=["cluster", "two-launch"])
+def gn_scheme(request):
+    """forward scheme of gd_group_norm_nhwc_fwd: one-launch cluster / DSMEM kernel (default) or the two-launch scheme"""
+    from geodiffuser_b200 import _lib
+
+    _lib.call("gd_group_norm_config", request.param)
+    yield request.param
+    _lib.call("gd_group_norm_config", 1)
+
+
 @pytest.mark.parametrize("shape", SHAPES)
 @pytest.mark.parametrize("silu,shift", [(False, False), (True, False), (True, True)])
-def test_group_norm_nhwc_forward_and_backward(shape, silu, shift):
+def test_group_norm_nhwc_forward_and_backward(shape, silu, shift, gn_scheme):
     from geodiffuser_b200 import body_ops
 
     B, C, H, W = shape
