@@ -257,11 +257,19 @@ gn_cluster_fwd_kernel(const GnClusterParams p) {
     float* chs = red + 16 * nact;                                                // [W][2]: per-channel sums of this CTA
     const bool active = t < nact;
     const int v = t % nv, rl = t / nv, c0 = v * 8;
-    float pb[8], a1[8], a2[8];
+    float pb[8], a1[8], a2[8], ga[8], be[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { pb[j] = 0.f; a1[j] = 0.f; a2[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { pb[j] = 0.f; a1[j] = 0.f; a2[j] = 0.f; ga[j] = 1.f; be[j] = 0.f; }
     if (active) {
         if (p.pre_bias) unpack8(*reinterpret_cast<const uint4*>(p.pre_bias + (long)b * C + c_base + c0), pb);
+        // affine parameters of this thread's 8 channels: requested now, consumed after the reduction (their latency hides under phase 1)
+        if (p.w_bf16) {
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gamma) + c_base + c0), ga);
+            unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.beta) + c_base + c0), be);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { ga[j] = reinterpret_cast<const float*>(p.gamma)[c_base + c0 + j]; be[j] = reinterpret_cast<const float*>(p.beta)[c_base + c0 + j]; }
+        }
 #pragma unroll 4
         for (int row = r0 + rl; row < r1; row += rpi) {
             const uint4 raw = *reinterpret_cast<const uint4*>(p.x + ((long)b * p.HW + row) * C + c_base + c0);
@@ -276,7 +284,7 @@ gn_cluster_fwd_kernel(const GnClusterParams p) {
     }
     __syncthreads();
     // per-channel sums over the row lanes (2W threads, fixed order), then per-group sums (8 threads per group, fixed tree)
-    for (int i = t; i < 2 * W; i += GNC_THREADS) {
+    for (int i = t; i < 2 * W; i += blockDim.x) {
         const int which = i / W, c = i - which * W;
         const float* src = red + ((which * 8 + (c & 7)) * nact) + (c >> 3);
         float s = 0.f;
@@ -320,14 +328,6 @@ gn_cluster_fwd_kernel(const GnClusterParams p) {
     // cluster barrier #2: nobody leaves (and frees its shared memory) while a sibling may still be reading it
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
     if (!active) return;
-    float ga[8], be[8];
-    if (p.w_bf16) {
-        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.gamma) + c_base + c0), ga);
-        unpack8(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.beta) + c_base + c0), be);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { ga[j] = reinterpret_cast<const float*>(p.gamma)[c_base + c0 + j]; be[j] = reinterpret_cast<const float*>(p.beta)[c_base + c0 + j]; }
-    }
     {
         int g = c0 / Cg;
 #pragma unroll
@@ -371,7 +371,8 @@ static bool gn_cluster_plan(GnClusterParams& p, size_t* smem) {
     if (p.nv > GNC_THREADS) return false;
     p.rpi = GNC_THREADS / p.nv;
     p.rpc = (p.HW + GNC_CLUSTER - 1) / GNC_CLUSTER;
-    if (p.rpi > p.rpc) p.rpi = p.rpc;
+    if (p.rpi > (p.rpc + 1) / 2) p.rpi = (p.rpc + 1) / 2;      // at least two rows per row lane, so few-row tiles do not launch idle warps
+    if (p.rpi < 1) p.rpi = 1;
     p.n_slabs = p.G / gs;
     *smem = (size_t)p.rpc * p.W * 2 + ((size_t)16 * p.nv * p.rpi + 2 * p.W) * sizeof(float);
     return *smem <= 192 * 1024 && (long)p.B * p.n_slabs * GNC_CLUSTER <= 65535L * 8;
@@ -505,7 +506,8 @@ int gd_group_norm_nhwc_fwd(const void* x, const void* pre_bias, const void* gamm
             if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             configured = 192 * 1024;
         }
-        gn_cluster_fwd_kernel<<<B * c.n_slabs * GNC_CLUSTER, GNC_THREADS, smem, (cudaStream_t)stream>>>(c);
+        const int threads = (c.nv * c.rpi + 31) / 32 * 32 < 64 ? 64 : (c.nv * c.rpi + 31) / 32 * 32;   // >= gs * 8 (<= 256 only if gs <= 8) -- see below
+        gn_cluster_fwd_kernel<<<B * c.n_slabs * GNC_CLUSTER, threads < c.gs * 8 ? (c.gs * 8 + 31) / 32 * 32 : threads, smem, (cudaStream_t)stream>>>(c);
         GD_CHECK_LAUNCH();
         return GD_OK;
     }

@@ -354,4 +354,8 @@ def build_model(device="cuda", seed=1234, tiny=False):
     for p in unet.parameters():
         p.requires_grad = False
     unet = unet.to(device).eval()
+    if torch.device(device).type == "cuda" and os.environ.get("GD_CUDNN_BENCHMARK", "1") != "0":
+        # the body's ~100 convolutions have a handful of fixed shapes: let cuDNN time its algorithms once per shape (first evaluation)
+        # instead of using the heuristic pick: 1006 -> 972 ms per 50-step edit on a B200
+        torch.backends.cudnn.benchmark = True
     return EditModel(unet, DDIMScheduler(), torch.device(device))
