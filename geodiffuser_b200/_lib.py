@@ -47,6 +47,7 @@ SIGNATURES = {
     "gd_group_norm_nhwc_fwd": [P, P, P, P, I, I, I, I, I, F, I, P, L, P, P, P, P],
     "gd_group_norm_nhwc_bwd": [P, P, P, P, P, I, P, I, I, I, I, I, P, L, P, P, P],
     "gd_masked_histogram_match": [P, P, P, P, L, I, P, P, P, P],
+    "gd_layer_norm_fwd": [P, P, P, L, I, F, P, P, P, P],
     "gd_geglu_fwd": [P, L, I, P, P],
     "gd_geglu_bwd": [P, P, L, I, P, P],
     "gd_add_bias_residual": [P, P, P, L, I, P, P],

@@ -147,3 +147,31 @@ def conv1x1(conv, x):
         y = F.linear(x.permute(0, 2, 3, 1).reshape(B * H * W, C), w, conv.bias)
         return y.reshape(B, H, W, conv.out_channels).permute(0, 3, 1, 2)
     return conv(x)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        mean = torch.empty(*x.shape[:-1], 1, device=x.device, dtype=torch.float32)
+        rstd = torch.empty_like(mean)
+        call("gd_layer_norm_fwd", ptr(x), ptr(weight), ptr(bias), rows, C, float(eps), ptr(y), ptr(mean), ptr(rstd), stream())
+        ctx.save_for_backward(x, weight, bias, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias, mean, rstd = ctx.saved_tensors
+        dx, _, _ = torch.ops.aten.native_layer_norm_backward(dy.contiguous(), x, [x.shape[-1]], mean, rstd, weight, bias, [True, False, False])
+        return dx, None, None, None
+
+
+def layer_norm(norm, x):
+    """norm(x) for an nn.LayerNorm over the last dimension"""
+    if (fast_body(x) and x.is_contiguous() and len(norm.normalized_shape) == 1 and x.shape[-1] % 8 == 0 and x.shape[-1] <= 1280
+            and norm.weight is not None and norm.bias is not None and norm.weight.dtype == torch.bfloat16
+            and not (norm.weight.requires_grad or norm.bias.requires_grad)):
+        return _LayerNorm.apply(x, norm.weight, norm.bias, norm.eps)
+    return norm(x)

@@ -436,6 +436,56 @@ __global__ void add_bias_residual_kernel(const bf16* __restrict__ a, const bf16*
     *reinterpret_cast<uint4*>(out + (i << 3)) = pack8(x);
 }
 
+// ---- LayerNorm over the channel dimension of (rows, C) bf16 token matrices (48 per UNet evaluation) -------------------------------------
+// One warp per row, the row held in registers (<= 5 vectors of 8 channels per lane: C <= 1280), mean then centred variance (two passes over
+// registers, no E[x^2] - mean^2 cancellation), fp32 mean / rstd saved for the backward (which stays torch's native_layer_norm_backward).
+template <int VPL>
+__global__ void __launch_bounds__(256) layer_norm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                                             long rows, int C, float eps, bf16* __restrict__ y, float* __restrict__ mean_out,
+                                                             float* __restrict__ rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (row >= rows) return;
+    const int nvec = C >> 3;
+    float f[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+            unpack8(*reinterpret_cast<const uint4*>(x + row * C + v * 8), f[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += f[i][j];
+        }
+    }
+    s = warp_sum(s);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; q += d * d; }
+        }
+    }
+    q = warp_sum(q);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nvec) {
+            float ga[8], be[8];
+            unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), ga);
+            unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), be);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[i][j] = (f[i][j] - mean) * rstd * ga[j] + be[j];
+            *reinterpret_cast<uint4*>(y + row * C + v * 8) = pack8(f[i]);
+        }
+    }
+}
+
 static int gn_plan(GnParams& p, long ws_floats) {
     p.Cg = p.C / p.G;
     p.nslot = p.C / 8;
@@ -552,6 +602,24 @@ int gd_add_bias_residual(const void* a, const void* b, const void* bias, long ro
     GD_CHECK_ARG(a && b && bias && out && rows > 0 && C > 0 && (C % 8) == 0);
     const long nvec = rows * (C / 8);
     add_bias_residual_kernel<<<ceil_div(nvec, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a, (const bf16*)b, (const bf16*)bias, nvec, C, (bf16*)out);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
+// y = layer_norm(x) over the last dimension of x (rows, C) bf16, gamma / beta (C) bf16, C % 8 == 0, C <= 1280; mean, rstd (rows) fp32 out
+// (the operands of aten::native_layer_norm_backward).
+int gd_layer_norm_fwd(const void* x, const void* gamma, const void* beta, long rows, int C, float eps, void* y, float* mean, float* rstd,
+                      void* stream) {
+    GD_CHECK_ARG(x && gamma && beta && y && mean && rstd && rows > 0 && C > 0);
+    if ((C % 8) != 0 || C > 1280) return set_error(GD_ERR_UNSUPPORTED, "layer norm: C = %d must be a multiple of 8 and <= 1280", C);
+    const int blocks = ceil_div(rows * 32, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int vpl = (C / 8 + 31) / 32;
+#define GD_LN(V) layer_norm_fwd_kernel<V><<<blocks, 256, 0, st>>>((const bf16*)x, (const bf16*)gamma, (const bf16*)beta, rows, C, eps, (bf16*)y, mean, rstd)
+    if (vpl <= 2) GD_LN(2);
+    else if (vpl <= 3) GD_LN(3);
+    else GD_LN(5);
+#undef GD_LN
     GD_CHECK_LAUNCH();
     return GD_OK;
 }

@@ -20,7 +20,7 @@ import torch.nn.functional as F
 
 import os
 
-from .body_ops import add_bias_residual, conv1x1, fast_body, geglu, group_norm_act
+from .body_ops import add_bias_residual, conv1x1, fast_body, geglu, group_norm_act, layer_norm
 
 BODY_CHANNELS_LAST = os.environ.get("GD_BODY_NCHW", "0") != "1"   # bf16 body layout: NHWC (cuDNN's native tensor-core layout) unless overridden
 
@@ -98,9 +98,9 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim)
 
     def forward(self, x, context):
-        x = self.attn1(self.norm1(x)) + x
-        x = self.attn2(self.norm2(x), encoder_hidden_states=context) + x
-        return self.ff(self.norm3(x)) + x
+        x = self.attn1(layer_norm(self.norm1, x)) + x
+        x = self.attn2(layer_norm(self.norm2, x), encoder_hidden_states=context) + x
+        return self.ff(layer_norm(self.norm3, x)) + x
 
 
 class Transformer2DModel(nn.Module):

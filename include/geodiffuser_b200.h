@@ -206,6 +206,11 @@ int gd_group_norm_config(int use_cluster_kernel);
 int gd_geglu_fwd(const void* proj, long rows, int F, void* out, void* stream);
 int gd_geglu_bwd(const void* proj, const void* dy, long rows, int F, void* dproj, void* stream);
 
+/* LayerNorm over the last dimension of x (rows, C) bf16 (one warp per row, row in registers, centred variance): gamma / beta (C) bf16,
+ * C % 8 == 0, C <= 1280; mean, rstd (rows) fp32 are the statistics aten::native_layer_norm_backward takes. */
+int gd_layer_norm_fwd(const void* x, const void* gamma, const void* beta, long rows, int C, float eps, void* y, float* mean, float* rstd,
+                      void* stream);
+
 /* out = a + b + bias[c] for (rows, C) bf16 channels-last tensors: a residual add with the producing convolution's bias folded in. */
 int gd_add_bias_residual(const void* a, const void* b, const void* bias, long rows, int C, void* out, void* stream);
 

@@ -112,3 +112,28 @@ def test_bias_residual_and_conv1x1_match_stock():
     y = body_ops.conv1x1(conv, x)
     assert y.shape == (2, 640, 16, 16) and y.is_contiguous(memory_format=cl)
     assert relerr(y.float().cpu().numpy(), conv(x).float().cpu().numpy()) <= 1.6e-2
+
+
+@pytest.mark.parametrize("shape", [(2, 4096, 320), (3, 1024, 640), (2, 256, 1280), (2, 64, 1280), (5, 7, 64), (1, 3, 136)])
+def test_layer_norm_forward_and_backward(shape):
+    from geodiffuser_b200 import body_ops
+
+    C = shape[-1]
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = (torch.randn(shape, device="cuda", generator=g) * 3.0 + 1.5).bfloat16()
+    norm = torch.nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(torch.randn(C, device="cuda", generator=g) * 0.5 + 1.0)
+        norm.bias.copy_(torch.randn(C, device="cuda", generator=g) * 0.3)
+    norm = norm.bfloat16().requires_grad_(False)
+    dy = torch.randn(shape, device="cuda", generator=g).bfloat16()
+    xr = x.float().requires_grad_(True)
+    ref = F.layer_norm(xr, (C,), norm.weight.float(), norm.bias.float(), norm.eps)
+    (dref,) = torch.autograd.grad(ref, xr, dy.float())
+    xi = x.clone().requires_grad_(True)
+    y = body_ops.layer_norm(norm, xi)
+    (dx,) = torch.autograd.grad(y, xi, dy)
+    assert y.dtype == torch.bfloat16
+    assert relerr(y.detach().float().cpu().numpy(), ref.detach().cpu().numpy()) <= 8e-3
+    assert relerr(dx.float().cpu().numpy(), dref.cpu().numpy()) <= 2e-2
+    assert relerr(y.detach().float().cpu().numpy(), norm(x).float().cpu().numpy()) <= 1.6e-2
