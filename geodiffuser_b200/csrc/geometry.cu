@@ -366,33 +366,12 @@ __global__ void __launch_bounds__(128) splat_composite_rows_kernel(const TIn* __
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
-        if (sizeof(TIn) == 2 && cnt <= 16) {
-            // all (<= 16) gathers of this output vector are requested before the first one is consumed: one L2 round trip instead of a
-            // chain of `cnt` dependent ones (the accumulation order is unchanged, so the result is too)
-            uint4 raw[16];
+        for (int k = 0; k < cnt; ++k) {
+            float f[8];
+            ld8<TIn>(s + (long)s_n[pl][k] * sp, f);
+            const float wk = s_w[pl][k];
 #pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < cnt) raw[k] = *reinterpret_cast<const uint4*>(s + (long)s_n[pl][k] * sp);
-#pragma unroll
-            for (int k = 0; k < 16; ++k)
-                if (k < cnt) {
-                    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[k]);
-                    const float wk = s_w[pl][k];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 t2 = __bfloat1622float2(h[j]);
-                        acc[2 * j] = __fadd_rn(acc[2 * j], __fmul_rn(wk, t2.x));
-                        acc[2 * j + 1] = __fadd_rn(acc[2 * j + 1], __fmul_rn(wk, t2.y));
-                    }
-                }
-        } else {
-            for (int k = 0; k < cnt; ++k) {
-                float f[8];
-                ld8<TIn>(s + (long)s_n[pl][k] * sp, f);
-                const float wk = s_w[pl][k];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(wk, f[j]));
-            }
+            for (int j = 0; j < 8; ++j) acc[j] = __fadd_rn(acc[j], __fmul_rn(wk, f[j]));
         }
         float q[8];
         const float m = blend ? blend[p] : 0.0f;
