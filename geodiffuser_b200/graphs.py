@@ -190,6 +190,26 @@ class GraphedGradPass:
         return self.g_lat, self.g_ctx
 
 
+def _prebuild_caches(model, controller, latents):
+    """Builds the controller's per-resolution caches (masks, splat index, inpaint rows, amodal tables: functional.ResolutionCache) for every
+    UNet level, as the first eager evaluation of an edit would.  Returns False if the processors are not the ones this package registers."""
+    tc = None
+    for proc in model.unet.attn_processors.values():
+        if getattr(proc, "controller", None) is controller and getattr(proc, "transform_coords", None) is not None:
+            tc = proc.transform_coords
+            break
+    if tc is None:
+        return False
+    dev = latents.device
+    controller._ensure_device_state(dev)
+    s0 = int(latents.shape[-1])
+    for f in (1, 2, 4, 8):
+        if s0 % f == 0:
+            controller._get_cache(s0 // f, tc, dev)
+    controller.eager_passes = max(1, getattr(controller, "eager_passes", 0))   # the shared cache buffers now belong to this edit
+    return True
+
+
 def grad_pass(model, controller, latents, context, t):
     """-> (d loss / d latents, d loss / d context) of one optimisation pass; controller.loss and controller.loss_log_dict hold the loss and its
     logged terms afterwards, as after the reference's diffusion_step(use_cfg=False).  `context` is the full [uncond, text] stack (the UNet sees
@@ -211,7 +231,21 @@ def grad_pass(model, controller, latents, context, t):
     weights = tuple(sorted((a, k, float(v)) for a in ("self", "cross") for k, v in lw[a].items() if k != "removal"))
     key = (controller_key(controller), weights, tuple(latents.shape), tuple(context.shape), id(model.unet))
     g = store.get(key)
+    # what a backward capture needs warmed up (cuBLAS / cuDNN handles and workspaces, cudnn.benchmark choices, the side stream's allocator
+    # cache) belongs to the process and the model, not to the edit: once one eager pass of this kind and shape has run on this model, the next
+    # edit captures its first optimisation pass directly -- after building its per-resolution caches, which synchronise and so cannot be
+    # built inside a capture
+    warmed = model.__dict__.setdefault("_grad_warm", set())
+    # (cuDNN's benchmark cache is keyed on these global switches as well: a capture after one of them changed would have to autotune inside
+    # the capture, which cuDNN cannot do)
+    cd = torch.backends.cudnn
+    wkey = (type(controller).__name__, tuple(latents.shape), tuple(context.shape), id(model.unet), cd.benchmark, cd.allow_tf32, cd.deterministic,
+            torch.backends.cuda.matmul.allow_tf32)
+    if g is None and wkey in warmed and _prebuild_caches(model, controller, latents):
+        g = store[key] = GraphedGradPass(model, latents, context, t)
+        return g(controller, latents, context, t)
     if g is None:
+        warmed.add(wkey)
         store[key] = "warm"
         side = _side_stream(model, dev)
         side.wait_stream(torch.cuda.current_stream(dev))

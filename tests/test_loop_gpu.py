@@ -11,6 +11,7 @@ by differences smaller than one bf16 ulp of the activations.  test_whole_network
 (edit latent perturbed by 0.3 sigma) the whole-network gradient agrees with the fp32 oracle to ~2e-2; on the kink it cannot.
 """
 import copy
+import math
 import os
 
 import numpy as np
@@ -147,7 +148,13 @@ def test_edit_is_deterministic(tiny_model):
 
     a = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4)
     b = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4)
-    assert torch.equal(a, b)
+    c = editor.perform_synthetic_edit(tiny_model, "rotate3d", num_ddim_steps=4)
+    # steady state (every pass of the edit replayed from graphs, the optimisation pass captured at its first occurrence): bit-identical
+    assert torch.equal(b, c)
+    # the first edit of a kind on a model runs its first optimisation pass eagerly (the warm-up a backward capture needs); under capture cuBLAS /
+    # cuDNN may pick other algorithms for the body's backward, so that edit agrees with the steady state to rounding, not to the bit
+    mse = float(((a.float() - b.float()) ** 2).mean())
+    assert mse == 0.0 or 10 * math.log10(float(b.float().abs().max()) ** 2 / mse) >= 40.0
 
 
 def test_cuda_graph_replay_matches_eager(tiny_model):
