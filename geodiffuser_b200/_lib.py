@@ -42,7 +42,7 @@ SIGNATURES = {
     "gd_splat_composite_rows": [P, I, P, P, P, I, I, I, I, F, F, P, I, P, I, P, P],
     "gd_ddim_step": [P, P, P, I, F, F, F, F, F, L, P, P, P],
     "gd_latent_update": [P, P, P, I, F, L, P, P],
-    "gd_norm_rescale": [P, L, F, P, P],
+    "gd_norm_rescale": [P, L, F, P, P, P],
     "gd_latent_blend": [P, P, P, I, I, L, P, P],
     "gd_group_norm_nhwc_fwd": [P, P, P, P, I, I, I, I, I, F, I, P, L, P, P, P, P],
     "gd_group_norm_nhwc_bwd": [P, P, P, P, P, I, P, I, I, I, I, I, P, L, P, P, P],

@@ -58,13 +58,15 @@ __global__ void latent_update_kernel(const float* __restrict__ lat, const float*
 }
 
 // x *= target_norm / sqrt(sum(x^2) + 1e-12); single block so the reduction order is fixed
-__global__ void __launch_bounds__(1024) norm_rescale_kernel(float* __restrict__ x, long n, float target_norm, float* __restrict__ norm_out) {
+__global__ void __launch_bounds__(1024) norm_rescale_kernel(float* __restrict__ x, long n, float target_norm, const float* __restrict__ target_dev,
+                                                            float* __restrict__ norm_out) {
     __shared__ float sh[32];
     float s = 0.f;
     for (long i = threadIdx.x; i < n; i += blockDim.x) s += x[i] * x[i];
     const float tot = block_sum(s, sh);
     const float nrm = sqrtf(tot + 1e-12f);
     if (norm_out && threadIdx.x == 0) *norm_out = nrm;
+    if (target_dev) target_norm = *target_dev;      // the target stays on the device: no host round trip between measuring and restoring a norm
     if (target_norm > 0.f) {
         const float f = target_norm / nrm;
         for (long i = threadIdx.x; i < n; i += blockDim.x) x[i] *= f;
@@ -106,9 +108,9 @@ int gd_latent_update(const float* lat, const float* grad, const float* mask, int
     return GD_OK;
 }
 
-int gd_norm_rescale(float* x, long n, float target_norm, float* norm_out, void* stream) {
+int gd_norm_rescale(float* x, long n, float target_norm, const float* target_dev, float* norm_out, void* stream) {
     GD_CHECK_ARG(x && n > 0);
-    norm_rescale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, target_norm, norm_out);
+    norm_rescale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, target_norm, target_dev, norm_out);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }

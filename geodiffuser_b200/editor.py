@@ -14,7 +14,7 @@ from .attention_processors import (AttentionGeometryEdit, AttentionGeometryRemov
                                    register_attention_control_diffusers, set_attn_processor_for_edit)
 from .diffusion import body_autocast, diffusion_step
 from .optimization import (_update_latent, adaptive_optimization_step_editing, adaptive_optimization_step_remover, apply_latent_update,
-                           norm_tensor, rescale_to_norm_)
+                           norm_tensor, norm_tensor_dev, rescale_to_norm_)
 from ._lib import call, ptr, stream
 
 NUM_DDIM_STEPS = 50
@@ -103,7 +103,7 @@ def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, gui
             l_eff = lr * (50 - i) * skip_optim_steps * (50 / (NUM_DDIM_STEPS + 1e-8))  # editor.py:207
             set_attn_processor_for_edit(model, coords_base=(0, 1), coords_edit=(1, 2), use_cfg=False)
             latents_in = latents.detach().float().requires_grad_(True)
-            orig_norm = norm_tensor(latents_in[-1:].detach())
+            orig_norm = norm_tensor_dev(latents_in[-1:].detach())   # stays on the device (no host sync in front of the optimisation pass)
             context_in = (context if context_save is None else context_save).detach().float().requires_grad_(True)
             for _ in range(num_optim_steps):
                 with torch.enable_grad():
@@ -241,6 +241,11 @@ def run_edit(model, staged, transform_in, edit_type="geometry_editor", num_ddim_
     controller, transform_coordinates = make_controller(model, staged, transform_in, edit_type, hp, num_ddim_steps)
     text, uncond, x0 = staged["text"], staged["uncond"], staged["x0"]
     model.scheduler.set_timesteps(num_ddim_steps)
+    # The per-resolution caches depend on the masks and the correspondence field only, and building them synchronises: do it now, before the
+    # inversion passes are queued, so that the host can record (capture) this edit's optimisation-pass graph while the GPU is still busy
+    # with the 50 inversion replays (graphs.grad_pass)
+    if graphs.ENABLED and graphs.GRAD_ENABLED and x0.is_cuda:
+        graphs.prebuild_caches(controller, transform_coordinates, device, int(x0.shape[-1]))
     if perform_ddim_inversion:
         ddim_latents = ddim_inversion_loop(model, x0, torch.cat([uncond[:1], text[:1]]), hp["guidance_scale"], num_ddim_steps)
     else:

@@ -8,6 +8,7 @@ bookkeeping only.  There is no CPU path.
 """
 import math
 
+import numpy as np
 import torch
 
 from . import _lib, geometry
@@ -177,7 +178,7 @@ def warp_queries(q_base, cache, lay=None, out=None):
         return geometry.splat_composite(q_base, cache.idx, cache.dist2, channels_last=True, blend_mask=cache.m_edit, out_dtype=torch.bfloat16)
     st = _lib.host_longs(lay.q)
     S = cache.S
-    r2 = float(geometry.np.float32(pow(geometry.splat_radius_ndc(S, None), 2)))
+    r2 = float(np.float32(pow(geometry.splat_radius_ndc(S, None), 2)))
     call("gd_splat_composite_rows", _lib.base_ptr(q_base), 1, st, ptr(cache.idx), ptr(cache.dist2), lay.h, lay.N, lay.d, cache.idx.shape[-1], r2,
          float(geometry.SPLATTER.tau), ptr(cache.m_edit), 0, _lib.base_ptr(out), 1, st, stream())
     return out

@@ -22,7 +22,7 @@ GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as 
 
 
 @contextlib.contextmanager
-def _capture(graph, pool, stream):
+def _capture(graph, pool, stream, sync=True):
     """Stream capture into `graph` on `stream`.  torch.cuda.graph() would also run gc.collect() and torch.cuda.empty_cache() first; an edit
     captures one graph per request, and an emptied allocator cache makes every eager allocation after it pay for cudaMalloc again, so the capture
     is driven by hand.  The cyclic garbage collector is paused: a collection in the middle of a capture may destroy an older CUDAGraph or free
@@ -30,7 +30,8 @@ def _capture(graph, pool, stream):
     was = gc.isenabled()
     gc.disable()
     cur = torch.cuda.current_stream(stream.device)
-    torch.cuda.synchronize(stream.device)
+    if sync:
+        torch.cuda.synchronize(stream.device)
     stream.wait_stream(cur)
     try:
         with torch.cuda.stream(stream):
@@ -152,7 +153,8 @@ class GraphedGradPass:
     log accumulator is a static buffer already.  Everything that changes between passes lives in device memory (the removal weight:
     controller.sync_device_weights) or in the key (all other weights, the controller flags)."""
 
-    def __init__(self, model, latents, context, t):
+    def __init__(self, model, latents, context, t, sync=True):
+        self.sync = sync            # False: record the graph without draining the device first (the GPU may still be running earlier passes)
         self.model = model          # (no reference to the controller: the graph is stored on it and must die with it, by refcount)
         self.latents = latents.detach().clone().requires_grad_(True)
         self.context = context.detach().clone().requires_grad_(True)
@@ -176,7 +178,7 @@ class GraphedGradPass:
             g = torch.cuda.CUDAGraph()
             step, layers = c.cur_step, c.loss_log_dict["num_layers"]
             l0 = _lib.LAUNCHES
-            with _capture(g, _pool(self.model), _side_stream(self.model, latents.device)):
+            with _capture(g, _pool(self.model), _side_stream(self.model, latents.device), sync=self.sync):
                 self.loss, self.g_lat, self.g_ctx = self._run(c)
             self.path_launches, _lib.LAUNCHES = _lib.LAUNCHES - l0, l0
             self.num_layers = c.loss_log_dict["num_layers"] - layers
@@ -190,24 +192,25 @@ class GraphedGradPass:
         return self.g_lat, self.g_ctx
 
 
-def _prebuild_caches(model, controller, latents):
+def prebuild_caches(controller, transform_coords, device, latent_size):
     """Builds the controller's per-resolution caches (masks, splat index, inpaint rows, amodal tables: functional.ResolutionCache) for every
-    UNet level, as the first eager evaluation of an edit would.  Returns False if the processors are not the ones this package registers."""
-    tc = None
-    for proc in model.unet.attn_processors.values():
-        if getattr(proc, "controller", None) is controller and getattr(proc, "transform_coords", None) is not None:
-            tc = proc.transform_coords
-            break
-    if tc is None:
+    UNet level, as the first eager evaluation of an edit would (a no-op for the levels that exist already)."""
+    if not hasattr(controller, "_get_cache"):
         return False
-    dev = latents.device
-    controller._ensure_device_state(dev)
-    s0 = int(latents.shape[-1])
+    controller._ensure_device_state(device)
     for f in (1, 2, 4, 8):
-        if s0 % f == 0:
-            controller._get_cache(s0 // f, tc, dev)
+        if latent_size % f == 0:
+            controller._get_cache(latent_size // f, transform_coords, device)
     controller.eager_passes = max(1, getattr(controller, "eager_passes", 0))   # the shared cache buffers now belong to this edit
     return True
+
+
+def _prebuild_caches(model, controller, latents):
+    """prebuild_caches with the correspondence field the registered processors hold; False if they are not this package's processors"""
+    for proc in model.unet.attn_processors.values():
+        if getattr(proc, "controller", None) is controller and getattr(proc, "transform_coords", None) is not None:
+            return prebuild_caches(controller, proc.transform_coords, latents.device, int(latents.shape[-1]))
+    return False
 
 
 def grad_pass(model, controller, latents, context, t):
@@ -242,7 +245,9 @@ def grad_pass(model, controller, latents, context, t):
     wkey = (type(controller).__name__, tuple(latents.shape), tuple(context.shape), id(model.unet), cd.benchmark, cd.allow_tf32, cd.deterministic,
             torch.backends.cuda.matmul.allow_tf32)
     if g is None and wkey in warmed and _prebuild_caches(model, controller, latents):
-        g = store[key] = GraphedGradPass(model, latents, context, t)
+        # recorded without a device synchronisation: when the caches were built before the inversion (editor.run_edit) nothing here waits for
+        # the GPU, so the ~45 ms of host work of the capture hide under the inversion replays still in flight
+        g = store[key] = GraphedGradPass(model, latents, context, t, sync=False)
         return g(controller, latents, context, t)
     if g is None:
         warmed.add(wkey)

@@ -11,14 +11,26 @@ def norm_tensor(A, eps=1e-12):
     """generic_torch.py:87 (returns a python float; one 4-byte D2H like the reference's .item())"""
     x = A.detach().float().contiguous().clone()
     out = torch.empty(1, device=x.device, dtype=torch.float32)
-    call("gd_norm_rescale", ptr(x), x.numel(), 0.0, ptr(out), stream())
+    call("gd_norm_rescale", ptr(x), x.numel(), 0.0, None, ptr(out), stream())
     return float(out)
+
+
+def norm_tensor_dev(A):
+    """the same norm as a 1-element device tensor: the edit loop only hands it back to rescale_to_norm_, so it never needs to reach the host
+    (the reference's .item() here is a device -> host sync in front of every optimisation step)"""
+    x = A.detach().float().contiguous().clone()
+    out = torch.empty(1, device=x.device, dtype=torch.float32)
+    call("gd_norm_rescale", ptr(x), x.numel(), 0.0, None, ptr(out), stream())
+    return out
 
 
 def rescale_to_norm_(x, target_norm):
     """in place: x *= target_norm / ||x||   (editor.py:316)"""
     assert x.is_contiguous() and x.dtype == torch.float32
-    call("gd_norm_rescale", ptr(x), x.numel(), float(target_norm), None, stream())
+    if torch.is_tensor(target_norm):
+        call("gd_norm_rescale", ptr(x), x.numel(), 0.0, ptr(target_norm.float().contiguous()), None, stream())
+    else:
+        call("gd_norm_rescale", ptr(x), x.numel(), float(target_norm), None, None, stream())
     return x
 
 

@@ -171,8 +171,9 @@ int gd_ddim_step(const float* x, const void* eps_u, const void* eps_c, int eps_i
 /* optimization.py:213-245: nan_to_num(grad); out = (lat - 2 m s g) - (1 - m) s g, m (hw) broadcast over channels (NULL: lat - s g). */
 int gd_latent_update(const float* lat, const float* grad, const float* mask, int hw, float step, long n, float* out, void* stream);
 
-/* editor.py:219,316 + generic_torch.py:87: norm_out = sqrt(sum x^2 + 1e-12); if target_norm > 0: x *= target_norm / norm. */
-int gd_norm_rescale(float* x, long n, float target_norm, float* norm_out, void* stream);
+/* editor.py:219,316 + generic_torch.py:87: norm_out = sqrt(sum x^2 + 1e-12); if target > 0: x *= target / norm, where target is
+ * *target_dev (device scalar) if given, else target_norm. */
+int gd_norm_rescale(float* x, long n, float target_norm, const float* target_dev, float* norm_out, void* stream);
 
 /* editor.py:393-399: out = a (1 - m) + m b, m optionally binarised (> 0.5). */
 int gd_latent_blend(const float* a, const float* b, const float* mask, int hw, int binarize, long n, float* out, void* stream);
