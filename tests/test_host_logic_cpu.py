@@ -117,3 +117,35 @@ def test_experiment_folder_format_round_trip(tmp_path):
     assert np.allclose(req["transform_in"].numpy(), T) and req["x0"].shape == (1, 4, 64, 64)
     shards = [runner.shard_round_robin(len(folders), r, 4) for r in range(4)]
     assert sorted(i for s in shards for i in s) == list(range(6))
+
+
+def test_projection_view_and_slab_strides():
+    """functional.ProjView presents the projection output (B, N, H*d) with the reference's (B*H, N, d) shape, and _Layout hands the kernels the
+    element strides of one (H, N, d) slab in either layout -- pure host logic, checked against explicit indexing"""
+    from geodiffuser_b200 import functional as Fn
+
+    B, N, Nk, H, d = 3, 10, 7, 4, 8
+    q = torch.arange(B * N * H * d, dtype=torch.float32).reshape(B, N, H * d)
+    k = torch.arange(B * Nk * H * d, dtype=torch.float32).reshape(B, Nk, H * d)
+    pv = Fn.ProjView(q, H)
+    assert tuple(pv.shape) == (B * H, N, d) and pv.dtype == q.dtype and pv.device == q.device and not pv.requires_grad
+    lay = Fn._Layout(q, k, H, True)
+    assert (lay.N, lay.Nk, lay.d) == (N, Nk, d) and lay.q == (H * d, d) and lay.kv == (H * d, d)
+    slab = lay.sl(q, 2)                                   # batch entry 2
+    flat = q.reshape(-1)
+    base = slab.storage_offset()
+    for h, n, c in ((0, 0, 0), (1, 3, 5), (3, 9, 7)):
+        assert flat[base + h * lay.q[1] + n * lay.q[0] + c] == q[2, n, h * d + c]
+    # the reference's head_to_batch_dim layout through the same descriptor
+    qh = q.reshape(B, N, H, d).permute(0, 2, 1, 3).reshape(B * H, N, d).contiguous()
+    kh = k.reshape(B, Nk, H, d).permute(0, 2, 1, 3).reshape(B * H, Nk, d).contiguous()
+    lay_h = Fn._Layout(qh, kh, H, False)
+    assert lay_h.q == (d, N * d) and lay_h.kv == (d, Nk * d)
+    slab_h = lay_h.sl(qh, 2)
+    base_h = slab_h.storage_offset()
+    flat_h = qh.reshape(-1)
+    for h, n, c in ((0, 0, 0), (1, 3, 5), (3, 9, 7)):
+        assert flat_h[base_h + h * lay_h.q[1] + n * lay_h.q[0] + c] == q[2, n, h * d + c]
+    assert tuple(lay.new_batch(q, 2, N).shape) == (2, N, H * d) and tuple(lay_h.new_batch(qh, 2, N).shape) == (2 * H, N, d)
+    st = lay.strides(out=lay.kv)
+    assert list(st) == [H * d, d, H * d, d, H * d, d]
