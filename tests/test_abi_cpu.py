@@ -69,3 +69,29 @@ def test_product_never_imports_oracle():
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), fn
             assert "from oracle" not in src and "import oracle" not in src, fn
+
+
+def test_stride_and_shape_validation_happens_before_any_launch():
+    """argument checks of the strided entry points return a status (no CUDA call is made, so this runs without a GPU): slab strides must be
+    positive multiples of 8 elements (16-byte rows for TMA / cp.async); the caller-side norms reject channel counts they do not serve"""
+    from geodiffuser_b200 import _lib
+
+    L = _lib.lib()
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    arr = (ctypes.c_void_p * 1)(p.value)
+    bad = (ctypes.c_long * 6)(40, 12, 40, 8, 40, 8)          # head stride 12: not a multiple of 8
+    rc = L.gd_attn_fwd_generic(arr, arr, arr, arr, arr, None, 1, 1, 8, 8, 8, ctypes.c_float(1.0), bad, 0, None)
+    assert rc == 1 and b"strides_ok" in L.gd_last_error()
+    rc = L.gd_attn_bwd(0, p, p, p, p, p, p, None, None, None, 8, 0, p, 1, 8, 8, 8, ctypes.c_float(1.0), bad, 0, None)
+    assert rc == 1
+    rc = L.gd_attn_fwd_sm100(arr, arr, arr, arr, arr, None, 1, 1, 100, 100, 40, ctypes.c_float(1.0), None, 0, None)
+    assert rc == 3 and b"N % 128" in L.gd_last_error()        # GD_ERR_UNSUPPORTED: shape outside the tcgen05 kernel's range
+    rc = L.gd_group_norm_nhwc_fwd(p, None, p, p, 1, 1, 16, 36, 4, ctypes.c_float(1e-5), 1, p, 1 << 20, p, p, p, None)
+    assert rc == 3 and b"multiple of 8" in L.gd_last_error()
+    rc = L.gd_layer_norm_fwd(p, p, p, 4, 2048, ctypes.c_float(1e-5), p, p, p, None)
+    assert rc == 3 and b"<= 1280" in L.gd_last_error()
+    rc = L.gd_splat_composite_rows(p, 1, None, p, p, 2, 16, 12, 15, ctypes.c_float(0.1), ctypes.c_float(1.0), None, 0, p, 1, None, None)
+    assert rc == 1                                            # C % 8 != 0
+    rc = L.gd_masked_histogram_match(p, p, p, p, 0, 3, p, p, p, None)
+    assert rc == 1                                            # npix == 0
