@@ -25,7 +25,7 @@ SIGNATURES = {
     "gd_morph": [P, I, I, I, I, I, P, P],
     "gd_attn_fwd_generic": [P, P, P, P, P, P, I, I, I, I, I, F, P, I, P],
     "gd_attn_fwd_sm100": [P, P, P, P, P, P, I, I, I, I, I, F, P, I, P],
-    "gd_attn_sm100_config": [I],
+    "gd_attn_sm100_config": [I, I],
     "gd_attn_bwd_prep": [P, I, P, P, P, P, P, P, P, I, I, I, I, P, P, P],
     "gd_attn_bwd": [I, P, P, P, P, P, P, P, P, P, I, I, P, I, I, I, I, F, P, I, P],
     "gd_attn_bwd_dk_split": [P, P, P, P, P, P, P, P, P, I, I, P, P, I, I, I, I, I, F, P, I, P],

@@ -178,9 +178,40 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     return d;
 }
 
+
+// ---- packed fp32x2 arithmetic (FFMA2 / FADD2 / FMUL2 on sm_100): one issue slot for two scores ---------------------------------------------
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ u64 pk2u(uint32_t lo, uint32_t hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// ex2_poly on a pair: 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA = 5 issue slots per score (the scalar form: 9)
+__device__ __forceinline__ u64 ex2_poly2(u64 x2) {
+    float x0, x1;
+    upk2(x2, x0, x1);
+    const u64 xc = pk2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f));
+    const u64 t = add2(xc, pk2(12582912.0f, 12582912.0f));
+    const u64 f = sub2(xc, sub2(t, pk2(12582912.0f, 12582912.0f)));
+    u64 p = fma2(f, pk2(0.0551716648f, 0.0551716648f), pk2(0.2426111251f, 0.2426111251f));
+    p = fma2(p, f, pk2(0.6932609677f, 0.6932609677f));
+    p = fma2(p, f, pk2(0.9999280572f, 0.9999280572f));
+    float p0, p1, t0, t1;
+    upk2(p, p0, p1);
+    upk2(t, t0, t1);
+    return pk2(__int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23)), __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23)));
+}
+// NP of every 8 score pairs go to the polynomial, spread evenly so that MUFU and FMA work interleave in program order
+template <int NP> __device__ __forceinline__ constexpr bool pair_is_poly(int c) {
+    return NP <= 0 ? false : NP == 1 ? (c % 8 == 7) : NP == 2 ? (c % 4 == 3) : NP == 3 ? (c % 8 == 2 || c % 8 == 5 || c % 8 == 7) : (c % 2 == 1);
+}
+
 // D = head_dim (40 or 80).  KB = number of 64-wide (128-byte) column blocks per operand row; KSTEPS = ceil(D/16); DV = O columns.
-// POLY: 0 = every exponential on the MUFU; n > 0 = every n-th exponential is evaluated by ex2_poly on the FMA pipe instead.
-template <int D, int POLY>
+// NP >= 0 (the product path): packed fp32x2 softmax arithmetic, NP of every 8 score pairs on the FMA-pipe polynomial, the rest on the MUFU.
+// NP < 0 (round-1 arithmetic, kept for A/B measurements): scalar ops, POLY = every POLY-th exponential on the polynomial (0 = none).
+template <int D, int POLY, int NP>
 __global__ void __launch_bounds__(SM100_THREADS, (D <= 64) ? 2 : 1)
 attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params p) {
     constexpr int KB = (D + 63) / 64;
@@ -317,18 +348,37 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
             const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
             m_run = m_new;
             float rs0 = 0.f, rs1 = 0.f;
+            u64 rsA = 0ull, rsB = 0ull;                           // packed row-sum accumulators (two chains)
+            const u64 sc2 = pk2(scale2, scale2), nm2 = pk2(-m_new, -m_new);
 #pragma unroll
             for (int cc = 0; cc < BN / 32; ++cc) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const int e = cc * 32 + 2 * c;
-                    const float x0 = fmaf(__uint_as_float(sr[e]), scale2, -m_new);
-                    const float x1 = fmaf(__uint_as_float(sr[e + 1]), scale2, -m_new);
-                    const float p0 = use_poly<POLY>(e) ? ex2_poly(x0) : ex2(x0);
-                    const float p1 = use_poly<POLY>(e + 1) ? ex2_poly(x1) : ex2(x1);
-                    rs0 += p0;
-                    rs1 += p1;
+                    float p0, p1;
+                    if constexpr (NP >= 0) {
+                        const u64 x2 = fma2(pk2u(sr[e], sr[e + 1]), sc2, nm2);
+                        u64 p2;
+                        if (pair_is_poly<NP>(c)) {
+                            p2 = ex2_poly2(x2);
+                            upk2(p2, p0, p1);
+                        } else {
+                            float x0, x1;
+                            upk2(x2, x0, x1);
+                            p0 = ex2(x0);
+                            p1 = ex2(x1);
+                            p2 = pk2(p0, p1);
+                        }
+                        if (c & 1) rsB = add2(rsB, p2); else rsA = add2(rsA, p2);
+                    } else {
+                        const float x0 = fmaf(__uint_as_float(sr[e]), scale2, -m_new);
+                        const float x1 = fmaf(__uint_as_float(sr[e + 1]), scale2, -m_new);
+                        p0 = use_poly<POLY>(e) ? ex2_poly(x0) : ex2(x0);
+                        p1 = use_poly<POLY>(e + 1) ? ex2_poly(x1) : ex2(x1);
+                        rs0 += p0;
+                        rs1 += p1;
+                    }
                     __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
                     pk[c] = *reinterpret_cast<uint32_t*>(&b2);
                 }
@@ -351,6 +401,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
                     }
                 }
                 tmem_st16(tmem + lane_off + COL_P + cc * 16, pk);
+            }
+            if constexpr (NP >= 0) {
+                float a0, a1;
+                upk2(add2(rsA, rsB), a0, a1);
+                rs0 = a0; rs1 = a1;
             }
             l_run = l_run * alpha + (rs0 + rs1);
             tmem_wait_st();
@@ -653,6 +708,227 @@ attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdP
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Backward, second form (the product path): same mathematics and operands as attn_bwd_sm100_kernel, re-tiled so that TWO CTAs share an SM.
+// 64-key steps: TMEM per CTA = S 64 + dP 64 + dS 32 + dQ <= 80 = 240 -> 256 columns; shared memory at head_dim 40 = Q 16 K + dO 16 K +
+// K ring 4 x 8 K + V ring 2 x 8 K = 80 KB.  The first form ran one CTA per SM: its two elementwise warps per sub-partition could not cover the
+// MUFU latency (50 % XU, 38 % issue, 2188 clk per 128-key step against 1024 clk of exponentials) and 256 CTAs on 148 SMs ran as two
+// waves; here 16 elementwise warps per SM are resident, all 256 CTAs of a 64^2 layer are co-resident (296 slots), and the per-score
+// arithmetic is packed (FFMA2 / FADD2 / FMUL2): 3 issue slots per score instead of 4.5.
+template <int D, int NP>
+__global__ void __launch_bounds__(SM100_BWD_THREADS, 2)
+attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdParams p) {
+    constexpr int KB = (D + 63) / 64;
+    constexpr int KSTEPS = (D + 15) / 16;
+    constexpr int DV = KSTEPS * 16;
+    constexpr int BNK = 64;                              // keys per step
+    constexpr int QTILE_BYTES = 128 * 128;               // one [128 rows][64 bf16] swizzled block of Q / dO
+    constexpr int KTILE_BYTES = BNK * 128;               // one [64 rows][64 bf16] swizzled block of K / V
+    constexpr int Q_BYTES = KB * QTILE_BYTES, K_BYTES = KB * KTILE_BYTES;
+    constexpr uint32_t COL_S = 0, COL_DP = 64, COL_DS = 128, COL_DQ = 160;
+    constexpr int TMEM_COLS = 256;
+    constexpr int NSTAGE = 2;                            // V ring
+    constexpr int KSTAGE = 4;                            // K ring (a K tile is read at both ends of its step)
+    constexpr int NEW = 8;                               // elementwise warps: (lane quarter, key half)
+    constexpr int NC = BNK / 2;                          // 32 key columns per elementwise thread
+
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sQ = smem;
+    unsigned char* sDO = sQ + Q_BYTES;
+    unsigned char* sK = sDO + Q_BYTES;
+    unsigned char* sV = sK + KSTAGE * K_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTAGE * K_BYTES);
+    uint64_t* q_full = bars + 0;
+    uint64_t* v_full = bars + 1;    // [2]
+    uint64_t* v_empty = bars + 3;   // [2]
+    uint64_t* s_full = bars + 5;
+    uint64_t* s_free = bars + 6;
+    uint64_t* ds_full = bars + 7;
+    uint64_t* dq_done = bars + 8;
+    uint64_t* k_full = bars + 9;              // [KSTAGE]
+    uint64_t* k_empty = bars + 9 + KSTAGE;    // [KSTAGE]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * KSTAGE);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, q0 = blockIdx.x * BM;
+    const int N = p.N;
+    const int nT = N / BNK;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+        for (int s = 0; s < KSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
+        mbar_init(s_full, 1); mbar_init(s_free, NEW); mbar_init(ds_full, NEW); mbar_init(dq_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == NEW + 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == NEW && lane == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.d_o); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == NEW) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            mbar_expect_tx(q_full, 2 * Q_BYTES);
+#pragma unroll
+            for (int b = 0; b < KB; ++b) {
+                tma_load_3d(sQ + b * QTILE_BYTES, &maps.q, q_full, b * 64, q0, h);
+                tma_load_3d(sDO + b * QTILE_BYTES, &maps.d_o, q_full, b * 64, q0, h);
+            }
+            for (int j = 0; j < nT; ++j) {
+                const int s = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                const int ks = j % KSTAGE;
+                const uint32_t kph = (j / KSTAGE) & 1;
+                mbar_wait_relaxed(k_empty + ks, kph ^ 1);
+                mbar_expect_tx(k_full + ks, K_BYTES);
+#pragma unroll
+                for (int b = 0; b < KB; ++b) tma_load_3d(sK + ks * K_BYTES + b * KTILE_BYTES, &maps.k, k_full + ks, b * 64, j * BNK, h);
+                mbar_wait_relaxed(v_empty + s, ph ^ 1);
+                mbar_expect_tx(v_full + s, K_BYTES);
+#pragma unroll
+                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * K_BYTES + b * KTILE_BYTES, &maps.v, v_full + s, b * 64, j * BNK, h);
+            }
+        }
+    } else if (warp == NEW + 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            constexpr uint32_t IDESC_SS = make_idesc(BM, BNK, 0, 0);
+            constexpr uint32_t IDESC_DQ = make_idesc(BM, DV, 0, 1);
+            const uint32_t aQ = smem_addr(sQ), aDO = smem_addr(sDO);
+            auto issue_scores = [&](int j) {
+                const int s = j & 1;
+                const int kst = j % KSTAGE;
+                mbar_wait(k_full + kst, (j / KSTAGE) & 1);
+                mbar_wait(v_full + s, (j >> 1) & 1);
+                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                tc_fence_after();
+                const uint32_t aK = smem_addr(sK + kst * K_BYTES), aV = smem_addr(sV + s * K_BYTES);
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks)
+                    umma_ss(tmem + COL_S, make_desc(aQ + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
+                            make_desc(aK + (ks >> 2) * KTILE_BYTES + (ks & 3) * 32, 16, 1024), IDESC_SS, ks > 0);
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ++ks)
+                    umma_ss(tmem + COL_DP, make_desc(aDO + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
+                            make_desc(aV + (ks >> 2) * KTILE_BYTES + (ks & 3) * 32, 16, 1024), IDESC_SS, ks > 0);
+                tc_commit(s_full);
+                tc_commit(v_empty + s);
+            };
+            mbar_wait(q_full, 0);
+            issue_scores(0);
+            for (int j = 0; j < nT; ++j) {
+                if (j + 1 < nT) issue_scores(j + 1);
+                const int s = j % KSTAGE;
+                mbar_wait(ds_full, j & 1);
+                tc_fence_after();
+                const uint32_t aK = smem_addr(sK + s * K_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < BNK / 16; ++kk)
+                    umma_ts(tmem + COL_DQ, tmem + COL_DS + kk * 8, make_desc(aK + kk * 2048, KTILE_BYTES, 1024), IDESC_DQ, (j > 0 || kk > 0));
+                tc_commit(dq_done);
+                tc_commit(k_empty + s);
+            }
+        }
+    } else {
+        // ================= elementwise warps 0-7 =================
+        const int quarter = warp & 3, half = warp >> 2;
+        const int row = q0 + quarter * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const float lse2 = p.lse[(long)h * N + row] * 1.4426950408889634f;
+        const float delta = p.delta[(long)h * N + row];
+        const u64 sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-lse2, -lse2), nd2 = pk2(-delta, -delta);
+        const int slot = p.rowmap ? p.rowmap[row] : -1;
+        const float ex_scale = (p.extra && p.extra_scale) ? *p.extra_scale : 1.0f;
+        const u64 es2 = pk2(ex_scale, ex_scale);
+        const float* exrow = (slot >= 0) ? p.extra + ((long)h * p.M + slot) * p.ex_ld + half * NC : nullptr;
+        for (int j = 0; j < nT; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            uint32_t sr[NC], dp[NC];
+            tmem_ld32(tmem + lane_off + COL_S + half * NC, sr);
+            tmem_ld32(tmem + lane_off + COL_DP + half * NC, dp);
+            tmem_wait_ld();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(s_free);
+            uint32_t pk[NC / 2];
+#pragma unroll
+            for (int c = 0; c < NC / 2; ++c) {
+                const int e = 2 * c;
+                const u64 x2 = fma2(pk2u(sr[e], sr[e + 1]), sc2, nl2);
+                u64 p2;
+                if (pair_is_poly<NP>(c)) {
+                    p2 = ex2_poly2(x2);
+                } else {
+                    float x0, x1;
+                    upk2(x2, x0, x1);
+                    p2 = pk2(ex2(x0), ex2(x1));
+                }
+                u64 g2 = pk2u(dp[e], dp[e + 1]);
+                if (exrow) {                                  // removal-loss rows: dL/dP of this row joins dP
+                    const float2 v = *reinterpret_cast<const float2*>(exrow + j * BNK + e);
+                    g2 = fma2(es2, pk2(v.x, v.y), g2);
+                }
+                float d0, d1;
+                upk2(mul2(p2, add2(g2, nd2)), d0, d1);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+                pk[c] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            if (j > 0) {
+                mbar_wait(dq_done, (j - 1) & 1);              // dS(j-1) has been consumed by its dQ product
+                tc_fence_after();
+            }
+            tmem_st16(tmem + lane_off + COL_DS + half * (NC / 2), pk);
+            tmem_wait_st();
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(ds_full);
+        }
+        // epilogue: dQ * scale -> global; the two warps of a quarter split the 16-column chunks
+        mbar_wait(dq_done, (nT - 1) & 1);
+        tc_fence_after();
+        unsigned char* og = reinterpret_cast<unsigned char*>(p.dq) + ((long)h * p.dq_hs + (long)row * p.dq_rs) * (p.dq_bf16 ? 2 : 4);
+        const float sc = p.scale;
+#pragma unroll
+        for (int c = 0; c < DV / 16; ++c) {
+            if ((c & 1) != half) continue;
+            uint32_t orr[16];
+            tmem_ld16(tmem + lane_off + COL_DQ + c * 16, orr);
+            tmem_wait_ld();
+            float f[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(orr[e]) * sc;
+            if (p.dq_bf16) {
+#pragma unroll
+                for (int e = 0; e < 16; e += 8)
+                    if (c * 16 + e < D) {
+                        uint4 v;
+                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[e], f[e + 1]), b1 = __floats2bfloat162_rn(f[e + 2], f[e + 3]);
+                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[e + 4], f[e + 5]), b3 = __floats2bfloat162_rn(f[e + 6], f[e + 7]);
+                        v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
+                        v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
+                        *reinterpret_cast<uint4*>(og + (c * 16 + e) * 2) = v;
+                    }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    if (c * 16 + e < D) *reinterpret_cast<float4*>(og + (c * 16 + e) * 4) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NEW + 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+    }
+}
+
 // ---- host side -------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -686,33 +962,38 @@ static int make_map(CUtensorMap* m, const void* base, int N, int H, int d, long 
     return GD_OK;
 }
 
-static int g_poly = 4;   // tuning knob (gd_attn_sm100_config): every g_poly-th exponential goes to the FMA pipe
+static int g_poly = 4;   // round-1 arithmetic only (g_np < 0): every g_poly-th exponential goes to the FMA pipe
+static int g_bwd_variant = 1, g_bwd_np = 0;
+static int g_np = 2;     // tuning knob (gd_attn_sm100_config): packed arithmetic, g_np of every 8 score pairs on the FMA-pipe polynomial
 
-template <int D, int POLY> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
+template <int D, int POLY, int NP> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
     constexpr int KB = (D + 63) / 64;
     const size_t smem = (size_t)5 * KB * 128 * 128 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D, POLY, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     dim3 grid(p.N / BM, p.H, G);
-    attn_fwd_sm100_kernel<D, POLY><<<grid, SM100_THREADS, smem, st>>>(maps, p);
+    attn_fwd_sm100_kernel<D, POLY, NP><<<grid, SM100_THREADS, smem, st>>>(maps, p);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }
 
 template <int D> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
-    switch (g_poly) {
-        case 0: return launch_sm100<D, 0>(maps, p, G, st);
-        case 2: return launch_sm100<D, 2>(maps, p, G, st);
-        case 3: return launch_sm100<D, 3>(maps, p, G, st);
-        case 4: return launch_sm100<D, 4>(maps, p, G, st);
-        case 6: return launch_sm100<D, 6>(maps, p, G, st);
-        case 8: return launch_sm100<D, 8>(maps, p, G, st);
+    switch (g_np) {
+        case 0: return launch_sm100<D, 0, 0>(maps, p, G, st);
+        case 1: return launch_sm100<D, 0, 1>(maps, p, G, st);
+        case 2: return launch_sm100<D, 0, 2>(maps, p, G, st);
+        case 3: return launch_sm100<D, 0, 3>(maps, p, G, st);
+        case 4: return launch_sm100<D, 0, 4>(maps, p, G, st);
     }
-    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for poly=%d", g_poly);
+    switch (g_poly) {
+        case 0: return launch_sm100<D, 0, -1>(maps, p, G, st);
+        case 4: return launch_sm100<D, 4, -1>(maps, p, G, st);
+    }
+    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for poly=%d np=%d", g_poly, g_np);
 }
 
 template <int D, int POLY> static int launch_bwd_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
@@ -729,6 +1010,32 @@ template <int D, int POLY> static int launch_bwd_sm100(const Sm100BwdMaps& maps,
     attn_bwd_sm100_kernel<D, POLY><<<grid, SM100_BWD_THREADS, smem, st>>>(maps, p);
     GD_CHECK_LAUNCH();
     return GD_OK;
+}
+
+template <int D, int NP> static int launch_bwd64_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
+    constexpr int KB = (D + 63) / 64;
+    const size_t smem = (size_t)2 * KB * 128 * 128 + (size_t)6 * KB * 64 * 128 + 256 + 1024;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_bwd64_sm100_kernel<D, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    dim3 grid(p.N / BM, p.H, 1);
+    attn_bwd64_sm100_kernel<D, NP><<<grid, SM100_BWD_THREADS, smem, st>>>(maps, p);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
+template <int D> static int dispatch_bwd64_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
+    switch (g_bwd_np) {
+        case 0: return launch_bwd64_sm100<D, 0>(maps, p, st);
+        case 1: return launch_bwd64_sm100<D, 1>(maps, p, st);
+        case 2: return launch_bwd64_sm100<D, 2>(maps, p, st);
+        case 3: return launch_bwd64_sm100<D, 3>(maps, p, st);
+        case 4: return launch_bwd64_sm100<D, 4>(maps, p, st);
+    }
+    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no backward instance for np=%d", g_bwd_np);
 }
 
 }  // namespace gd
@@ -762,13 +1069,20 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
     return dispatch_sm100<80>(maps, p, G, (cudaStream_t)stream);
 }
 
-// Tuning knob of the tcgen05 forward (process-wide): poly in {0, 2, 3, 4, 6, 8} = every poly-th exponential of the online softmax is
-// evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (0: all MUFU).  Default 4.
-extern "C" int gd_attn_sm100_config(int poly) {
-    if (!(poly == 0 || poly == 2 || poly == 3 || poly == 4 || poly == 6 || poly == 8))
-        return set_error(GD_ERR_INVALID, "gd_attn_sm100_config(poly=%d): poly in {0,2,3,4,6,8}", poly);
-    g_poly = poly;
-    return GD_OK;
+// Tuning knobs of the tcgen05 kernels (process-wide; not part of the reference surface).
+//   key 0  fwd: packed fp32x2 softmax arithmetic with `value` in 0..4 of every 8 score pairs on the FMA-pipe polynomial (default 2);
+//               value -1 selects the round-1 scalar arithmetic (A/B measurements), whose polynomial share is key 1
+//   key 1  fwd, scalar arithmetic only: every value-th exponential on the polynomial, value in {0, 4}
+//   key 2  bwd: 0 = round-1 kernel (128-key steps, one CTA per SM), 1 = 64-key steps, two CTAs per SM, packed arithmetic (default)
+//   key 3  bwd variant 1: value in 0..4 of every 8 score pairs on the polynomial (default 0)
+extern "C" int gd_attn_sm100_config(int key, int value) {
+    switch (key) {
+        case 0: if (value < -1 || value > 4) break; g_np = value; return GD_OK;
+        case 1: if (value != 0 && value != 4) break; g_poly = value; return GD_OK;
+        case 2: if (value < 0 || value > 1) break; g_bwd_variant = value; return GD_OK;
+        case 3: if (value < 0 || value > 4) break; g_bwd_np = value; return GD_OK;
+    }
+    return set_error(GD_ERR_INVALID, "gd_attn_sm100_config(key=%d, value=%d): see include/geodiffuser_b200.h", key, value);
 }
 
 // dQ of softmax(scale q k^T) v for the self-attention levels (N == Nk, N % 128 == 0, d in {40, 80}); same operands as gd_attn_bwd mode 0.
@@ -786,8 +1100,9 @@ extern "C" int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, co
     int rc;
     if ((rc = make_map(&maps.q, q, N, H, d, q_rs, q_hs, BM)) != GD_OK) return rc;
     if ((rc = make_map(&maps.d_o, d_o, N, H, d, d, (long)N * d, BM)) != GD_OK) return rc;
-    if ((rc = make_map(&maps.k, k, N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
-    if ((rc = make_map(&maps.v, v, N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
+    const int key_rows = g_bwd_variant == 1 ? 64 : BN;      // keys per step of the selected kernel = TMA box rows of K / V
+    if ((rc = make_map(&maps.k, k, N, H, d, kv_rs, kv_hs, key_rows)) != GD_OK) return rc;
+    if ((rc = make_map(&maps.v, v, N, H, d, kv_rs, kv_hs, key_rows)) != GD_OK) return rc;
     Sm100BwdParams p;
     p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.dq = dq;
     p.dq_rs = strides ? strides[4] : d; p.dq_hs = strides ? strides[5] : (long)N * d; p.dq_bf16 = dq_is_bf16;
@@ -796,6 +1111,7 @@ extern "C" int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, co
     cudaStream_t st = (cudaStream_t)stream;
     // all exponentials on the MUFU: with ~4.5 instructions per score the elementwise warps are issue-bound, the polynomial only adds to that
     // (measured: 110.9 us vs 124.6 us at H=8, N=4096, d=40)
+    if (g_bwd_variant == 1) return d == 40 ? dispatch_bwd64_sm100<40>(maps, p, st) : dispatch_bwd64_sm100<80>(maps, p, st);
     if (d == 40) return launch_bwd_sm100<40, 0>(maps, p, st);
     return launch_bwd_sm100<80, 0>(maps, p, st);
 }

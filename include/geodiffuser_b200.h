@@ -83,9 +83,12 @@ int gd_attn_fwd_sm100(const void* const* q_host, const void* const* k_host, cons
                       void* const* lse_host, void* const* os_host, int G, int H, int N, int Nk, int d, float scale,
                       const long* strides_host, int os_is_bf16, void* stream);
 
-/* Tuning knob of gd_attn_fwd_sm100 (process-wide, not part of the reference surface): poly in {0,2,3,4,6,8} = every poly-th exponential
- * of the online softmax is evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (0 = all MUFU; default 4). */
-int gd_attn_sm100_config(int poly);
+/* Tuning knobs of the tcgen05 kernels (process-wide, not part of the reference surface).  key 0: forward, `value` in 0..4 of every 8
+ * score pairs of the online softmax evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (packed fp32x2 arithmetic;
+ * default 2; -1 = round-1 scalar arithmetic with key 1 = every value-th exponential on the polynomial, value in {0, 4});
+ * key 2: backward kernel, 0 = 128-key steps / one CTA per SM, 1 = 64-key steps / two CTAs per SM (default); key 3: polynomial share of
+ * backward variant 1 (0..4 of 8 pairs, default 0). */
+int gd_attn_sm100_config(int key, int value);
 
 /* ---- (3) backward, fused with the attention-map losses --------------------------------------------------------------- */
 

@@ -104,35 +104,46 @@ def bwd_case(H, N, d, M=0, sm100=False):
           flush=True)
 
 
+cfg = lambda key, value: call("gd_attn_sm100_config", key, value)
+
 if only == "sweep":
-    for poly in (0, 8, 6, 4, 3, 2):
-        if True:
-            call("gd_attn_sm100_config", poly)
-            print(f"--- poly={poly}", flush=True)
-            fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
-            fwd_case("gd_attn_fwd_sm100", 5, 8, 4096, 40)
-            fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
-            fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
+    for np_ in (-1, 0, 1, 2, 3, 4):
+        cfg(0, np_)
+        print(f"--- fwd: {'round-1 scalar arithmetic, poly=4' if np_ < 0 else f'packed arithmetic, {np_}/8 pairs on the polynomial'}", flush=True)
+        fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_sm100", 4, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
+        fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
+    cfg(0, 2)
+    for variant, nps in ((0, (0,)), (1, (0, 1, 2, 3))):
+        for np_ in nps:
+            cfg(2, variant)
+            cfg(3, np_)
+            print(f"--- bwd: variant {variant} ({'128-key steps, 1 CTA/SM' if variant == 0 else f'64-key steps, 2 CTA/SM, {np_}/8 pairs on the polynomial'})", flush=True)
+            bwd_case(8, 4096, 40, sm100=True)
+            bwd_case(8, 4096, 40, M=410, sm100=True)
+            bwd_case(8, 1024, 80, sm100=True)
+            bwd_case(8, 1024, 80, M=100, sm100=True)
+            bwd_case(2, 9216, 40, sm100=True)
+    cfg(2, 1)
+    cfg(3, 0)
 if only in (None, "fwd"):
     fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
-    fwd_case("gd_attn_fwd_sm100", 5, 8, 4096, 40)
+    fwd_case("gd_attn_fwd_sm100", 4, 8, 4096, 40)
     fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
-    fwd_case("gd_attn_fwd_sm100", 5, 8, 1024, 80)
+    fwd_case("gd_attn_fwd_sm100", 4, 8, 1024, 80)
     if not quick:
         fwd_case("gd_attn_fwd_sm100", 3, 8, 9216, 40, check=False)
         fwd_case("gd_attn_fwd_generic", 3, 8, 4096, 40)
         fwd_case("gd_attn_fwd_generic", 3, 8, 256, 160)
 if only in (None, "bwd"):
-    for poly in (0, 4):
-        call("gd_attn_sm100_config", poly)
-        print(f"--- poly={poly}")
-        bwd_case(8, 4096, 40, sm100=True)
-        bwd_case(8, 4096, 40, M=410, sm100=True)
-        bwd_case(8, 1024, 80, sm100=True)
-        bwd_case(8, 1024, 80, M=100, sm100=True)
-        bwd_case(2, 9216, 40, sm100=True)
-    bwd_case(8, 4096, 40)
-    bwd_case(8, 4096, 40, M=410)
-    bwd_case(8, 1024, 80)
+    bwd_case(8, 4096, 40, sm100=True)
+    bwd_case(8, 4096, 40, M=410, sm100=True)
+    bwd_case(8, 1024, 80, sm100=True)
+    bwd_case(8, 1024, 80, M=100, sm100=True)
+    bwd_case(2, 9216, 40, sm100=True)
     if not quick:
+        bwd_case(8, 4096, 40)
+        bwd_case(8, 4096, 40, M=410)
+        bwd_case(8, 1024, 80)
         bwd_case(8, 256, 160)

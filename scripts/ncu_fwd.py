@@ -1,13 +1,13 @@
-"""one launch of the tcgen05 forward at the 64^2 level for `ncu --set full` (argv: poly [G N d])"""
+"""one launch of the tcgen05 forward at the 64^2 level for `ncu --set full` (argv: np [G N d]; np = pairs of 8 on the polynomial, -1 = round-1 arithmetic)"""
 import sys
 import torch
 sys.path.insert(0, ".")
 from geodiffuser_b200 import _lib
 from geodiffuser_b200._lib import call, stream
-poly = int(sys.argv[1])
+np_ = int(sys.argv[1])
 G, N, d = (int(a) for a in sys.argv[2:5]) if len(sys.argv) > 4 else (3, 4096, 40)
 H = 8
-call("gd_attn_sm100_config", poly)
+call("gd_attn_sm100_config", 0, np_)
 g = torch.Generator(device="cuda").manual_seed(1)
 mk = lambda: (torch.randn(H, N, d, device="cuda", generator=g) * 1.5).bfloat16()
 qs = [mk() for _ in range(G)]
