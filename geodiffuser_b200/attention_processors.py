@@ -306,8 +306,13 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
             tc = torch.as_tensor(np.asarray(tc))
         return tc.to(device=device, dtype=torch.float32).contiguous()
 
+    def _ensure_dilated(self, device):
+        """the remover dilates its image mask in the constructor (:986); the editor does not"""
+
     def _ensure_mask_new_warped(self, transform_coords, device):
-        """editor.py:147-149 / attention_processors.py:517-523: binarised forward-splat of the object mask at image resolution."""
+        """editor.py:147-149 / attention_processors.py:517-523: binarised forward-splat of the object mask at image resolution
+        (the controller's image mask as its constructor left it: dilated by 5 px for the remover, :986)."""
+        self._ensure_dilated(device)
         if self.mask_new_warped is None:
             tc = self._coords512(transform_coords, device)[:1]
             img_mask = self.image_mask.to(device=device, dtype=torch.float32)
@@ -328,6 +333,11 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         if q.shape[0] % n_entries == 0 and q.shape[0] // n_entries != h:
             h = q.shape[0] // n_entries               # batch without the dead unconditional reference sample (diffusion.diffusion_step)
         if not (is_cross or (self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1])):
+            if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
+                # the reference back-propagates through compute_attention here (:646-647); the batch driver never optimises past the
+                # self-replace window (optimize_steps < self_replace_steps), and the plain kernel is forward-only: refuse, do not drop it
+                raise NotImplementedError("gradient through a self-attention layer outside the self-replace window "
+                                          "(optimize_steps > self_replace_steps) is not served by this path")
             return Fn.plain_attention(q, k, v, scale, h)
         self._ensure_device_state(q.device)
         N = q.shape[1]
@@ -432,12 +442,16 @@ class AttentionGeometryRemover(_GeometryControllerBase):
         self.initialize_default_loss_weights()
         self.initialize_loss_log_dict()
 
+    def _ensure_dilated(self, device):
+        """:986 -- done once, on first device use, whichever of the warped-mask build (editor.py:148) and the first attention call comes first"""
+        if not self._dilated:
+            self.image_mask = geometry.torch_dilate(self.image_mask.to(device=device, dtype=torch.float32)[:, None], 5)[:, 0]
+            self._dilated = True
+
     def _get_cache(self, S, transform_coords, device):
         c = self._res_cache.get(S)
         if c is None:
-            if not self._dilated:
-                self.image_mask = geometry.torch_dilate(self.image_mask.to(device=device, dtype=torch.float32)[:, None], 5)[:, 0]
-                self._dilated = True
+            self._ensure_dilated(device)
             masks = geometry.build_masks(self.image_mask[-1].contiguous(), None, None, S)
             c = Fn.ResolutionCache(S, masks, coords_S=None, need_amodal=False, arena=self._arena)
             self._res_cache[S] = c

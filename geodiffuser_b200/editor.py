@@ -135,7 +135,7 @@ def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, gui
                 context = best_context.detach()
                 context_save = context
         elif i < fast_start_steps * n_t:
-            continue
+            pass    # editor.py:354-355: only the diffusion step is skipped; the reference-latent replacement and the fast-start warp below still run
         elif context_save is not None:
             context = context_save
         # the reference latent is overwritten below whenever the inversion trajectory is given, which makes its unconditional evaluation dead work
@@ -144,8 +144,9 @@ def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, gui
             set_attn_processor_for_edit(model, coords_base=(1, 2), coords_edit=(2, 3), use_cfg=True)
         else:
             set_attn_processor_for_edit(model, coords_base=(2, 3), coords_edit=(3, 4), use_cfg=True)
-        latents = diffusion_step(model, controller, latents, context, t, guidance_scale, transform_coords=transform_coordinates,
-                                 skip_uncond_reference=skip)
+        if not i < fast_start_steps * n_t:
+            latents = diffusion_step(model, controller, latents, context, t, guidance_scale, transform_coords=transform_coordinates,
+                                     skip_uncond_reference=skip)
         if ddim_latents is not None:
             i_n = len(ddim_latents) - 2 - i
             latents = torch.cat([ddim_latents[i_n].to(latents), latents[-1:].detach()], 0)  # editor.py:375-377

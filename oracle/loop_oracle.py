@@ -171,7 +171,9 @@ def geometry_inputs(kind, synth):
     g = O.corr_build(depth.copy(), mask.copy(), T)
     amodal = O.erode3(O.mesh_mask(g["coords"], g["mask"]))
     idx512, _, d2 = O.splat_index(g["coords"][None])
-    mnw = O.binarize(O.splat_composite(mask.astype(np.float32)[None, None], idx512, d2))[0, 0]
+    # editor.py:147-149 warps controller.image_mask, which the remover's constructor has dilated by 5 px (attention_processors.py:986)
+    src = O.dilate(mask.astype(np.float32), 5) if kind == "remove" else mask.astype(np.float32)
+    mnw = O.binarize(O.splat_composite(np.asarray(src, np.float32)[None, None], idx512, d2))[0, 0]
     return dict(coords=g["coords"], mask=mask.astype(np.float32), amodal=amodal, mnw=mnw)
 
 

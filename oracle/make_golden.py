@@ -123,8 +123,10 @@ def make_ref_controller(R, kind, mask, geo, num_steps=50, obj_edit_step=0.9):
     return c
 
 
-def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_step=0):
-    print(f"== attention case {name}")
+def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_step=0, subsample=0):
+    """subsample > 0 (the UNet's real shapes, H = 8: full arrays would be ~10 MB each): `out`, `dq`, `dq_loss` are stored for the token rows
+    `rows` = every subsample-th row plus every inpaint row (where the removal-loss gradient lives), not for all N."""
+    print(f"== attention case {name}", flush=True)
     c = make_ref_controller(R, kind, geo["mask"], geo)
     c.cur_step = cur_step
     B = 4 if use_cfg else 2
@@ -136,7 +138,20 @@ def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_ste
     tc = torch.from_numpy(geo["coords"])[None]
     with torch.set_grad_enabled(not use_cfg):
         out_ref = c(q, k, v, is_cross, "down", transform_coords=tc, scale=scale, mask=None)
-    rec = dict(out=out_ref.detach().numpy())
+    rows = None
+    if subsample:
+        if kind == "edit":
+            inp = O.build_masks(geo["mask"], geo["mnw"][0, 0].numpy(), geo["amodal"], S)["mask_1_empty"]
+        else:       # remover: the inpaint set is the resized dilated object mask (attention_processors.py:860-866)
+            inp = O.binarize(O.resize_bilinear(O.binarize(O.dilate(geo["mask"], 5))[None], S)[0])
+        keep = np.zeros(S * S, bool)
+        keep[::subsample] = True
+        keep |= np.asarray(inp).reshape(-1) > 0.5
+        rows = np.nonzero(keep)[0].astype(np.int32)
+    sub = (lambda a: a[:, rows]) if subsample else (lambda a: a)
+    rec = dict(out=sub(out_ref.detach().numpy()))
+    if subsample:
+        rec["rows"] = rows
     # oracle restatement
     q2, k2, v2 = (a.detach().clone().requires_grad_(not use_cfg) for a in (q, k, v))
     blend = cur_step < int(50 * 0.9)
@@ -148,18 +163,27 @@ def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_ste
         else:
             res = O.remover_layer(q2, k2, v2, is_cross, scale, H, c.coords_base, c.coords_edit,
                                   O.dilate(geo["mask"], 5), use_cfg, blend)
-    check("out", res["out"].detach().numpy(), rec["out"], 2e-5)
+    check("out", sub(res["out"].detach().numpy()), rec["out"], 2e-5)
     if not use_cfg and S >= 32:
         loss_ref = c.loss
+        # the gradient of the loss ALONE (what the optimisation pass back-propagates: the loss layers' own contribution), then the mixed one
+        lq, lk = torch.autograd.grad(loss_ref, [q, k], allow_unused=True, retain_graph=True)
+        l2q, l2k = torch.autograd.grad(res["loss"], [q2, k2], allow_unused=True, retain_graph=True)
         gq, gk = torch.autograd.grad(loss_ref + 0.37 * out_ref.sum(), [q, k], allow_unused=True)
         g2q, g2k = torch.autograd.grad(res["loss"] + 0.37 * res["out"].sum(), [q2, k2], allow_unused=True)
         check("loss", res["loss"].item(), loss_ref.item(), 2e-5)
         check("dq", g2q.numpy(), gq.numpy(), 1e-4)
+        check("dq (loss alone)", l2q.numpy(), lq.numpy(), 1e-4)
         rec["loss"] = np.float64(loss_ref.item())
-        rec["dq"] = gq.numpy()
+        rec["dq"] = sub(gq.numpy())
+        rec["dq_loss"] = sub(lq.numpy())
+        rec["dq_loss_absmax"] = np.float64(np.abs(lq.numpy()).max())
+        rec["dq_absmax"] = np.float64(np.abs(gq.numpy()).max())
         if gk is not None:
             check("dk", g2k.numpy(), gk.numpy(), 1e-4)
             rec["dk"] = gk.numpy()
+            if lk is not None:
+                rec["dk_loss"] = lk.numpy()
         for key, val in c.loss_log_dict["cross" if is_cross else "self"].items():
             rec["term_" + key] = np.float64(float(val))
             check("term " + key, float(res["terms"][key]), float(val), 5e-5)
@@ -213,8 +237,40 @@ def main():
     attention_case(R, "remove_cross_S32_opt", geos["remove"], "remove", 32, 2, 16, True, False, 108)
     attention_case(R, "remove_self_S32_cfg_late", geos["remove"], "remove", 32, 2, 16, False, True, 109, cur_step=46)
     elementwise_case(R)
+    product_shape_cases(R, geos)
     print("golden vectors written to", OUT)
 
 
+def product_shape_cases(R, geos=None):
+    """The layers bench.py times: SD-1.5 self-attention at the 64^2 level (H = 8, head_dim 40) and the 32^2 level (head_dim 80) -- the shapes the
+    tcgen05 kernels serve -- through the reference's own controllers (attention_processors.py:513-624, 842-928); plus one 768^2-input layer
+    (S = 96, N = 9216; H = 2 keeps the CPU run in memory)."""
+    if geos is None:
+        geos = {name: geometry_only(R, name) for name in ("translate2d", "rotate3d", "remove")}
+    attention_case(R, "edit_self_S64_H8d40_opt", geos["rotate3d"], "edit", 64, 8, 40, False, False, 201, subsample=16)
+    attention_case(R, "edit_self_S64_H8d40_cfg", geos["rotate3d"], "edit", 64, 8, 40, False, True, 202, subsample=16)
+    attention_case(R, "remove_self_S64_H8d40_opt", geos["remove"], "remove", 64, 8, 40, False, False, 203, subsample=16)
+    attention_case(R, "edit_self_S32_H8d80_opt", geos["translate2d"], "edit", 32, 8, 80, False, False, 204, subsample=8)
+    attention_case(R, "remove_self_S32_H8d80_opt", geos["remove"], "remove", 32, 8, 80, False, False, 205, subsample=8)
+
+
+def geometry_only(R, cfg):
+    """what geometry_case returns, without re-writing its golden file"""
+    image, depth, mask, T = synth.edit_inputs(cfg)
+    (pimg, valid, dproj, coords_ref, pmask_ref), d_used, mask_t = R.get_transform_coordinates_cpu(
+        image / 255.0, depth.copy(), mask.copy(), T, return_mesh=True)
+    coords_ref = coords_ref[0].numpy()
+    g = O.corr_build(depth.copy(), mask.copy(), T)
+    amodal = O.erode3(O.mesh_mask(g["coords"], g["mask"]))
+    tc = torch.from_numpy(coords_ref)[None]
+    image_mask2 = torch.from_numpy(mask.astype(np.float32))[None].tile(2, 1, 1)
+    t_coords_m = R.gt.reshape_transform_coords(tc, in_mat_shape=image_mask2.shape).tile(2, 1, 1, 1)
+    mnw_ref = R.gt.binarize_tensor(R.wu.warp_grid_edit(image_mask2[:, None], t_coords_m))
+    return dict(coords=coords_ref, mask=mask, mnw=mnw_ref, amodal=amodal)
+
+
 if __name__ == "__main__":
+    if "--product-shapes" in sys.argv:     # only the H = 8 cases (the rest of the golden set is left untouched)
+        torch.set_grad_enabled(True)
+        sys.exit(product_shape_cases(load_reference()))
     sys.exit(main())

@@ -91,10 +91,11 @@ def run_case(name, kind, tiny, num_steps, pin, R, inversion=True, step_limit=Non
 def main():
     torch.set_num_threads(os.cpu_count())
     R = load_reference()
+    only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None     # e.g. --only remove
     if "--full-only" not in sys.argv:
-        run_case("translate2d_tiny", "translate2d", True, 10, True, R)
-        run_case("rotate3d_tiny", "rotate3d", True, 10, True, R)
-        run_case("remove_tiny", "remove", True, 10, True, R)
+        for kind in ("translate2d", "rotate3d", "remove"):
+            if only in (None, kind):
+                run_case(f"{kind}_tiny", kind, True, 10, True, R)
     if "--full" in sys.argv or "--full-only" in sys.argv:
         run_case("translate2d_full5", "translate2d", False, 5, False, R, inversion=False)
 
