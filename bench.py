@@ -28,6 +28,12 @@ WORKLOAD = "configs[1]: SD-1.5 random-init, 512x512, 50-step DDIM inversion + 3D
 N_OPT, N_CFG, N_INV = 17, 50, 50   # UNet passes per edit with the perform_exp hyper-parameters (large_scale_editor.py:290-299)
 
 
+def bench_config(n):
+    """the same dict in both arms (the driver compares them)"""
+    return {"workload": WORKLOAD, "parallelism": f"request-level dp{n} (independent edits, no collective)",
+            "l2": "no flush needed: every UNet pass streams 1.7 GB of weights + activations (> 126 MB L2) between repeats"}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -80,13 +86,85 @@ class ClockSampler:
         return out
 
 
-def kernel_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full` capture"""
+def kernel_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed `ncu --set full` capture of this round"""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_kernel_traffic.json")) as f:
-            return json.load(f)["attn_fwd_sm100_kernel<40> G=3 H=8 N=4096"]["dram_bytes_per_launch"]
+        with open(os.path.join(ROOT, "profiles", "r02_kernel_traffic.json")) as f:
+            return json.load(f)[key]["dram_bytes_per_launch"]
     except Exception:
         return None
+
+
+def kernel_rooflines(dev, M64, M32, peaks, iters=60):
+    """The dominant kernels of the path, timed EAGERLY in this process at the shapes the edit launches them with (the edit itself replays
+    CUDA graphs, inside which launches cannot carry events): CUDA events on the launching stream around `iters` back-to-back launches
+    after 5 warm-up launches, cycling through enough distinct operand sets that consecutive launches never find their inputs in the
+    126 MB L2.  Algorithmic work per launch: SURVEY 8(d) (forward 4*G*H*N^2*d, backward 6*H*N^2*d, correlation 2*H*M*N^2).
+    Peak: the BURST bf16 figure of MEASURED_PEAKS.json (kernel timed alone); `frac_sustained` uses the sustained one."""
+    from geodiffuser_b200 import _lib
+    from geodiffuser_b200._lib import call, ptr, stream
+
+    H = 8
+    burst, sust = peaks["bf16_tflops"], peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+    gen = torch.Generator(device=dev).manual_seed(4321)
+    mk = lambda *shape, s=1.5: (torch.randn(*shape, device=dev, generator=gen) * s).bfloat16()
+
+    def timed(fns):
+        for i in range(5):
+            fns[i % len(fns)]()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fns[i % len(fns)]()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    def entry(name, kernel, flops, ms, **extra):
+        ach = flops / (ms * 1e-3) / 1e12
+        return dict(kernel=kernel, entry=name, bound="tensor", achieved=ach, peak=burst, unit="TFLOP/s", frac=ach / burst, frac_sustained=ach / sust,
+                    avg_launch_ms=ms, launches=iters, algorithmic_flops_per_launch=flops, **extra)
+
+    out = []
+    for G, N, d in ((3, 4096, 40), (4, 4096, 40), (3, 1024, 80), (4, 1024, 80)):
+        nsets = max(2, int(140e6 // ((G + 2) * H * N * d * 2)) + 1)
+        fns = []
+        for _ in range(nsets):
+            qs, k, v = [mk(H, N, d) for _ in range(G)], mk(H, N, d), mk(H, N, d)
+            O = torch.empty(G, H, N, d, device=dev, dtype=torch.float32)
+            L = torch.empty(G, H, N, device=dev, dtype=torch.float32)
+            a = (_lib.ptr_array(qs), _lib.ptr_array([k] * G), _lib.ptr_array([v] * G), _lib.ptr_array([O[i] for i in range(G)]),
+                 _lib.ptr_array([L[i] for i in range(G)]))
+            fns.append(lambda a=a, keep=(qs, k, v, O, L), G=G, N=N, d=d: call("gd_attn_fwd_sm100", *a, None, G, H, N, N, d, float(d ** -0.5), None, 0, stream()))
+        ms = timed(fns)
+        out.append(entry("gd_attn_fwd_sm100", f"attn_fwd_sm100_kernel<{d}> G={G} H={H} N={N}", 4.0 * G * H * N * N * d, ms, operand_sets=nsets,
+                         traffic=kernel_traffic(f"attn_fwd_sm100_kernel<{d}> G={G} H={H} N={N}")))
+        del fns
+    for N, d, M in ((4096, 40, M64), (4096, 40, 0), (1024, 80, M32)):
+        nsets = max(2, int(140e6 // (4 * H * N * d * 2 + M * H * N * 4)) + 1)
+        fns = []
+        ld = (N + 7) // 8 * 8
+        for _ in range(nsets):
+            q, k, v, do = mk(H, N, d), mk(H, N, d), mk(H, N, d), mk(H, N, d, s=1.0)
+            L = (torch.randn(H, N, device=dev, generator=gen) * 0.1 + 8.0).float()
+            delta = torch.randn(H, N, device=dev, generator=gen).float() * 0.01
+            dq = torch.empty(H, N, d, device=dev, dtype=torch.float32)
+            extra = rowmap = dl = None
+            if M:
+                rows = torch.arange(N, device=dev)[(torch.arange(N, device=dev) // 64 % 3 == 1)][:M].int()      # clustered rows, like an object mask
+                rowmap = torch.full((N,), -1, device=dev, dtype=torch.int32)
+                rowmap[rows.long()] = torch.arange(rows.numel(), device=dev, dtype=torch.int32)
+                extra = torch.randn(H, rows.numel(), ld, device=dev, generator=gen) * 0.01
+                dl = torch.ones(1, device=dev)
+            fns.append(lambda q=q, k=k, v=v, do=do, L=L, delta=delta, dq=dq, extra=extra, rowmap=rowmap, dl=dl, N=N, d=d, M=M, ld=ld:
+                       call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld,
+                            int(extra.shape[1]) if extra is not None else 0, ptr(dq), H, N, d, float(d ** -0.5), None, 0, stream()))
+        ms = timed(fns)
+        out.append(entry("gd_attn_bwd_sm100", f"attn_bwd64_sm100_kernel<{d}> H={H} N={N} removal rows M={M}", 6.0 * H * N * N * d, ms, operand_sets=nsets,
+                         traffic=kernel_traffic(f"attn_bwd64_sm100_kernel<{d}> H={H} N={N}")))
+        del fns
+    return out
 
 
 def attn_flops(tag):
@@ -140,7 +218,7 @@ def run_reference(args):
     sample = "1 DDIM-inversion UNet eval + 1 optimisation pass (fwd+bwd) + 1 CFG pass of configs[1], extrapolated x(50, 17, 50)"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "edits/s", "n_gpus": args.gpus, "steps": len(per_edit),
             "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": sample},
+            "data": "synthetic", "config": bench_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": "edits/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "edits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -193,45 +271,43 @@ def run_ours(args):
     resident = lambda: editor.run_edit(model, staged, req["transform_in"], req["edit_type"])
     sampler = ClockSampler(local)
     sampler.start()
-    _lib.profile_begin(["gd_attn_fwd_sm100", "gd_attn_fwd_generic", "gd_attn_bwd", "gd_attn_bwd_sm100", "gd_attn_probs", "gd_corr_max_partial"])
-    l0 = _lib.LAUNCHES
+    l0, f0 = _lib.LAUNCHES, _lib.FLOPS
     ms_value = timed(resident, args.steps)
     launches = _lib.LAUNCHES - l0
-    prof = _lib.profile_end()
+    flops_per_edit = (_lib.FLOPS - f0) / args.steps     # algorithmic attention-path FLOP (graph replays re-count what they captured)
     clocks = sampler.stop()
     # (2) end to end through the public API with host buffers (H2D of the request + D2H of the result inside the timed region)
     ms_e2e = timed(api, args.steps)
 
+    # (3) roofline of the path's dominant kernels at the shapes of this edit (eager, outside the timed regions)
+    roofs = None
     if rank == 0:
         peaks, peak_src = measured_peaks()
+        ctrl, tc = editor.make_controller(model, staged, req["transform_in"], req["edit_type"], dict(editor.EXP_PARAMS[req["edit_type"]]))
+        M64, M32 = (ctrl._get_cache(S, tc, dev).M for S in (64, 32))
+        del ctrl
+        roofs = kernel_rooflines(dev, M64, M32, peaks)
+        if not roofs:
+            raise SystemExit("bench.py: the roofline leg produced nothing")
+
+    if rank == 0:
         value = world * args.steps / (ms_value / 1e3)
         e2e = world * args.steps / (ms_e2e / 1e3)
-        # roofline of the dominant kernel: the tcgen05 forward at the 64^2 level (N = 4096, d = 40), timed live above
-        by_kernel = {k: sum(ms for ms, _ in v) for k, v in prof.items()}
-        dom = [(ms, tag) for ms, tag in prof.get("gd_attn_fwd_sm100", []) if tag and tag[2] == 4096]
-        roof = None
-        if dom:
-            fl = sum(attn_flops(t) for _, t in dom)
-            ms = sum(m for m, _ in dom)
-            ach = fl / (ms * 1e-3) / 1e12
-            pk = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-            roof = {"kernel": "attn_fwd_sm100_kernel<40> (N=4096, d=40)", "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s",
-                    "frac": ach / pk, "traffic": kernel_traffic(), "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
-                    "launches": len(dom), "avg_launch_ms": ms / len(dom), "algorithmic_flops_per_launch": fl / len(dom),
-                    "share_of_step_ms": {k: round(v / args.steps, 3) for k, v in by_kernel.items()}}
-            bw = [(ms, tag) for ms, tag in prof.get("gd_attn_bwd_sm100", []) if tag and tag[1] == 4096]
-            if bw:   # the matching backward (dQ) at the same level, same peak: 6*H*N^2*d algorithmic FLOP per launch
-                flb = sum(6.0 * t[0] * t[1] * t[1] * t[2] for _, t in bw)
-                msb = sum(m for m, _ in bw)
-                roof["backward"] = {"kernel": "attn_bwd_sm100_kernel<40> (N=4096, d=40)", "achieved": flb / (msb * 1e-3) / 1e12, "unit": "TFLOP/s",
-                                    "frac": flb / (msb * 1e-3) / 1e12 / pk, "launches": len(bw), "avg_launch_ms": msb / len(bw)}
+        roof = dict(roofs[0])
+        roof["peak_source"] = peak_src + ": burst bf16 (kernel timed alone, back to back); frac_sustained = against the sustained figure"
+        roof["other_kernels"] = roofs[1:]
+        pk_s = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
+        # the whole edit against the attention roofline (north_star): algorithmic attention-path FLOP of one edit / step time / peak
+        roof["edit_level"] = {"attention_path_flops_per_edit": flops_per_edit,
+                              "attention_roofline_frac_of_edit": flops_per_edit / (ms_value / args.steps * 1e-3) / 1e12 / pk_s,
+                              "peak": pk_s, "note": "whole-edit time (UNet body included) against the sustained bf16 peak; per GPU, identical at every N (weak scaling)"}
         line = {"metric": METRIC, "value": value, "unit": "edits/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": WORKLOAD, "parallelism": f"request-level dp{world} (independent edits, no collective)",
-                           "l2": "no flush needed: every UNet pass streams 1.7 GB of weights + activations (> 126 MB L2) between repeats"},
+                "config": bench_config(world),
                 "e2e": {"value": e2e, "unit": "edits/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof}
+        assert line["roofline"] is not None and line["roofline"]["frac"] > 0
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count()
             parts, t_edit = cpu_reference_sample(threads)

@@ -104,9 +104,31 @@ def profile_end():
     return out
 
 
+FLOPS = 0.0  # algorithmic FLOP of the attention-path contractions launched by this process (SURVEY 8(d) formulas; bench.py: share of the roofline)
+
+
+def algorithmic_flops(name, tag):
+    """forward 4*G*H*N*Nk*d (QK^T + PV per stream), backward 6*H*N*Nk*d (recompute S, dP, dQ or dK), removal correlation
+    2*H*M*N*Nk.  `tag` = the shape tuple the caller passes with the launch."""
+    if tag is None:
+        return 0.0
+    if name in ("gd_attn_fwd_sm100", "gd_attn_fwd_generic"):
+        G, H, N, Nk, d = tag
+        return 4.0 * G * H * N * Nk * d
+    if name in ("gd_attn_bwd_sm100", "gd_attn_bwd", "gd_attn_bwd_dk_split"):
+        H, N, Nk, d = tag
+        return 6.0 * H * N * Nk * d
+    if name in ("gd_corr_max_partial", "gd_removal_corr_sm100"):
+        H, M, N, Nk = tag
+        return 2.0 * H * M * N * Nk
+    return 0.0      # (gd_attn_probs re-materialises map rows for the correlation: implementation work, not in SURVEY 8(d)'s count)
+
+
 def call(name, *args, tag=None):
-    global LAUNCHES
+    global LAUNCHES, FLOPS
     L_ = lib()
+    if tag is not None:
+        FLOPS += algorithmic_flops(name, tag)
     if PROFILE is not None and name in PROFILE["names"] and not torch.cuda.is_current_stream_capturing():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

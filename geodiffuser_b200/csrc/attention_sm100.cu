@@ -462,265 +462,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
 }
 
 // ---------------------------------------------------------------------------------------------------------------------------
-// Forward, second form: same tiles, operands, TMEM layout and MMA / TMA roles as attn_fwd_sm100_kernel, but EIGHT softmax warps per CTA:
-// two threads share a query row (TMEM lane), 64 key columns each.  ncu of the first form (profiles/r02_attn_fwd_np2_ncu.md): MUFU 56 %,
-// issue 49 %, tensor 28 % -- nothing saturated; 2.7 warps per scheduler, 5.6 clk per issued instruction: the two softmax warps per
-// sub-partition cannot cover the handshake latencies (s_full / pv_done waits ~420 clk, tcgen05.ld, the serial row max) that precede
-// each tile's 768 clk of exponentials.  Four warps per sub-partition, each holding 64 instead of 128 scores (half the live registers,
-// twice the ILP), keep the MUFU fed while their neighbours wait.  The row max of the two halves is exchanged through shared memory
-// behind a 64-thread named barrier (the two warps of a lane quarter); every other decision (grow, alpha) is then identical in both.
-constexpr int SM100_FWD8_THREADS = 320;
-
-template <int D, int NP>
-__global__ void __launch_bounds__(SM100_FWD8_THREADS, (D <= 64) ? 2 : 1)
-attn_fwd8_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params p) {
-    constexpr int KB = (D + 63) / 64;
-    constexpr int KSTEPS = (D + 15) / 16;
-    constexpr int DV = KSTEPS * 16;
-    constexpr int TILE_BYTES = 128 * 128;
-    constexpr int OP_BYTES = KB * TILE_BYTES;
-    constexpr int TMEM_COLS = (192 + DV <= 256) ? 256 : 512;
-    constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
-    constexpr int NSTAGE = 2;
-    constexpr int NSW = 8;                          // softmax warps
-    constexpr int NC = BN / 2;                      // 64 key columns per softmax thread
-
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sQ = smem;
-    unsigned char* sK = sQ + OP_BYTES;
-    unsigned char* sV = sK + NSTAGE * OP_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTAGE * OP_BYTES);
-    uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;    // [2]
-    uint64_t* k_empty = bars + 3;   // [2]
-    uint64_t* v_full = bars + 5;    // [2]
-    uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;
-    uint64_t* s_free = bars + 10;
-    uint64_t* p_full = bars + 11;
-    uint64_t* pv_done = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-    float* xch = reinterpret_cast<float*>(bars + 16);   // [2 parities][2 halves][128 rows]: half-row maxima (later: half-row sums)
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
-    const int N = p.N;
-    const int nT = N / BN;
-
-    if (threadIdx.x == 0) {
-        mbar_init(q_full, 1);
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
-        mbar_init(s_full, 1); mbar_init(s_free, NSW); mbar_init(p_full, NSW); mbar_init(pv_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == NSW + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp == NSW && lane == 0) { tma_prefetch_desc(&maps.q[g]); tma_prefetch_desc(&maps.k[g]); tma_prefetch_desc(&maps.v[g]); }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == NSW) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            mbar_expect_tx(q_full, OP_BYTES);
-#pragma unroll
-            for (int b = 0; b < KB; ++b) tma_load_3d(sQ + b * TILE_BYTES, &maps.q[g], q_full, b * 64, q0, h);
-            for (int j = 0; j < nT; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait_relaxed(k_empty + s, ph ^ 1);
-                mbar_expect_tx(k_full + s, OP_BYTES);
-#pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_3d(sK + s * OP_BYTES + b * TILE_BYTES, &maps.k[g], k_full + s, b * 64, j * BN, h);
-                mbar_wait_relaxed(v_empty + s, ph ^ 1);
-                mbar_expect_tx(v_full + s, OP_BYTES);
-#pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v[g], v_full + s, b * 64, j * BN, h);
-            }
-        }
-    } else if (warp == NSW + 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t IDESC_QK = make_idesc(BM, BN, 0, 0);
-            constexpr uint32_t IDESC_PV = make_idesc(BM, DV, 0, 1);
-            const uint32_t aQ = smem_addr(sQ);
-            auto issue_qk = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(k_full + s, (j >> 1) & 1);
-                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
-                tc_fence_after();
-                const uint32_t aK = smem_addr(sK + s * OP_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tmem + COL_S, make_desc(aQ + off, 16, 1024), make_desc(aK + off, 16, 1024), IDESC_QK, ks > 0);
-                }
-                tc_commit(s_full);
-                tc_commit(k_empty + s);
-            };
-            mbar_wait(q_full, 0);
-            issue_qk(0);
-            for (int j = 0; j < nT; ++j) {
-                if (j + 1 < nT) issue_qk(j + 1);
-                const int s = j & 1;
-                mbar_wait(v_full + s, (j >> 1) & 1);
-                mbar_wait(p_full, j & 1);
-                tc_fence_after();
-                const uint32_t aV = smem_addr(sV + s * OP_BYTES);
-#pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk)
-                    umma_ts(tmem + COL_O, tmem + COL_P + kk * 8, make_desc(aV + kk * 2048, TILE_BYTES, 1024), IDESC_PV, (j > 0 || kk > 0));
-                tc_commit(pv_done);
-                tc_commit(v_empty + s);
-            }
-        }
-    } else {
-        // ================= softmax warps 0-7: (lane quarter, key half) =================
-        const int quarter = warp & 3, half = warp >> 2;
-        const int rloc = quarter * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        const float scale2 = p.scale2;
-        const int pair_bar = 1 + quarter;             // named barrier of the two warps that share this lane quarter
-        float m_run = -INFINITY, l_run = 0.f;
-        for (int j = 0; j < nT; ++j) {
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            uint32_t sr[NC];
-            tmem_ld32(tmem + lane_off + COL_S + half * NC, sr);
-            tmem_ld32(tmem + lane_off + COL_S + half * NC + 32, sr + 32);
-            tmem_wait_ld();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(s_free);
-            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < NC; c += 8) {
-                mx0 = max3(mx0, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
-                mx1 = max3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
-                mx2 = max3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
-                mx3 = max3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
-            }
-            const float mine = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-            float* xm = xch + (j & 1) * 256;
-            xm[half * 128 + rloc] = mine;
-            asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-            const float mx = fmaxf(mine, xm[(half ^ 1) * 128 + rloc]);
-            const float m_cand = fmaxf(m_run, mx * scale2);
-            const bool grow = (m_cand - m_run) > 8.0f;
-            const float m_new = grow ? m_cand : m_run;
-            const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
-            m_run = m_new;
-            u64 rsA = 0ull, rsB = 0ull;
-            const u64 sc2 = pk2(scale2, scale2), nm2 = pk2(-m_new, -m_new);
-#pragma unroll
-            for (int cc = 0; cc < NC / 32; ++cc) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int e = cc * 32 + 2 * c;
-                    const u64 x2 = fma2(pk2u(sr[e], sr[e + 1]), sc2, nm2);
-                    u64 p2;
-                    float p0, p1;
-                    if (pair_is_poly<NP>(c)) {
-                        p2 = ex2_poly2(x2);
-                        upk2(p2, p0, p1);
-                    } else {
-                        float x0, x1;
-                        upk2(x2, x0, x1);
-                        p0 = ex2(x0);
-                        p1 = ex2(x1);
-                        p2 = pk2(p0, p1);
-                    }
-                    if (c & 1) rsB = add2(rsB, p2); else rsA = add2(rsA, p2);
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-                    pk[c] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-                if (cc == 0 && j > 0) {
-                    // P(j) may overwrite P(j-1), and O may be corrected, only once PV(j-1) has completed (waited for behind the first
-                    // half of the exponentials, where the MMA round trip p_full -> PV -> commit is already covered)
-                    mbar_wait(pv_done, (j - 1) & 1);
-                    tc_fence_after();
-                    if (__any_sync(0xffffffffu, grow)) {
-#pragma unroll
-                        for (int c = 0; c < DV / 16; ++c) {
-                            if ((c & 1) != half) continue;        // the two threads of a row split the O chunks
-                            uint32_t orr[16];
-                            tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
-                            tmem_st16(tmem + lane_off + COL_O + c * 16, orr);
-                        }
-                    }
-                }
-                tmem_st16(tmem + lane_off + COL_P + half * (NC / 2) + cc * 16, pk);
-            }
-            float a0, a1;
-            upk2(add2(rsA, rsB), a0, a1);
-            l_run = l_run * alpha + (a0 + a1);
-            tmem_wait_st();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(p_full);
-        }
-        // epilogue: combine the two half-row sums, O / l -> global, lse
-        float* xs = xch + (nT & 1) * 256;             // the parity the last tile did not use
-        xs[half * 128 + rloc] = l_run;
-        asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
-        const float l_tot = l_run + xs[(half ^ 1) * 128 + rloc];
-        mbar_wait(pv_done, (nT - 1) & 1);
-        tc_fence_after();
-        const int row = q0 + rloc;
-        const float inv = 1.0f / l_tot;
-        float* og = p.o[g] ? p.o[g] + ((long)h * N + row) * D : nullptr;
-        unsigned char* sg = p.os[g] ? reinterpret_cast<unsigned char*>(p.os[g]) + ((long)h * p.os_hs + (long)row * p.os_rs) * (p.os_bf16 ? 2 : 4) : nullptr;
-#pragma unroll
-        for (int c = 0; c < DV / 16; ++c) {
-            if ((c & 1) != half) continue;
-            uint32_t orr[16];
-            tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
-            tmem_wait_ld();
-            float f[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(orr[e]) * inv;
-            if (og) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 4)
-                    if (c * 16 + e < D) *reinterpret_cast<float4*>(og + c * 16 + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-            }
-            if (sg) {
-                if (p.os_bf16) {
-#pragma unroll
-                    for (int e = 0; e < 16; e += 8)
-                        if (c * 16 + e < D) {
-                            uint4 v;
-                            __nv_bfloat162 b0 = __floats2bfloat162_rn(f[e], f[e + 1]), b1 = __floats2bfloat162_rn(f[e + 2], f[e + 3]);
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(f[e + 4], f[e + 5]), b3 = __floats2bfloat162_rn(f[e + 6], f[e + 7]);
-                            v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
-                            v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
-                            *reinterpret_cast<uint4*>(sg + (c * 16 + e) * 2) = v;
-                        }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 16; e += 4)
-                        if (c * 16 + e < D) *reinterpret_cast<float4*>(sg + (c * 16 + e) * 4) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-                }
-            }
-        }
-        if (half == 0) p.lse[g][(long)h * N + row] = (m_run + log2f(l_tot)) * 0.6931471805599453f;
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == NSW + 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------------------------
 // Subsystem (3): the matching BACKWARD for the self-attention levels, dQ only -- on this path every K / V is the detached base sample's
 // (attention_sharing.py:242), so dK / dV do not exist for self layers.  Replaces autograd through compute_attention + bmm
 // (materialised (H, N, N) maps kept for backward in the reference) and, through `extra`, the removal-loss term's dense `dcorr . A_b`.
@@ -1223,7 +964,6 @@ static int make_map(CUtensorMap* m, const void* base, int N, int H, int d, long 
 
 static int g_poly = 4;   // round-1 arithmetic only (g_np < 0): every g_poly-th exponential goes to the FMA pipe
 static int g_bwd_variant = 1, g_bwd_np = 0;
-static int g_fwd_variant = 1;   // 0 = four softmax warps (one thread per row), 1 = eight (two threads per row)
 static int g_np = 2;     // tuning knob (gd_attn_sm100_config): packed arithmetic, g_np of every 8 score pairs on the FMA-pipe polynomial
 
 template <int D, int POLY, int NP> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
@@ -1241,32 +981,7 @@ template <int D, int POLY, int NP> static int launch_sm100(const Sm100Maps& maps
     return GD_OK;
 }
 
-template <int D, int NP> static int launch_fwd8_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
-    constexpr int KB = (D + 63) / 64;
-    const size_t smem = (size_t)5 * KB * 128 * 128 + 128 + 2048 + 1024;     // operands + barriers + max / sum exchange + alignment slack
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd8_sm100_kernel<D, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
-    dim3 grid(p.N / BM, p.H, G);
-    attn_fwd8_sm100_kernel<D, NP><<<grid, SM100_FWD8_THREADS, smem, st>>>(maps, p);
-    GD_CHECK_LAUNCH();
-    return GD_OK;
-}
-
 template <int D> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
-    if (g_fwd_variant == 1) {
-        switch (g_np) {
-            case 0: return launch_fwd8_sm100<D, 0>(maps, p, G, st);
-            case 1: return launch_fwd8_sm100<D, 1>(maps, p, G, st);
-            case 2: return launch_fwd8_sm100<D, 2>(maps, p, G, st);
-            case 3: return launch_fwd8_sm100<D, 3>(maps, p, G, st);
-            case 4: return launch_fwd8_sm100<D, 4>(maps, p, G, st);
-        }
-        return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: forward variant 1 needs key 0 in 0..4 (got %d)", g_np);
-    }
     switch (g_np) {
         case 0: return launch_sm100<D, 0, 0>(maps, p, G, st);
         case 1: return launch_sm100<D, 0, 1>(maps, p, G, st);
@@ -1360,14 +1075,12 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
 //   key 1  fwd, scalar arithmetic only: every value-th exponential on the polynomial, value in {0, 4}
 //   key 2  bwd: 0 = round-1 kernel (128-key steps, one CTA per SM), 1 = 64-key steps, two CTAs per SM, packed arithmetic (default)
 //   key 3  bwd variant 1: value in 0..4 of every 8 score pairs on the polynomial (default 0)
-//   key 4  fwd: 0 = four softmax warps per CTA (one thread per query row), 1 = eight (two threads per row; default)
 extern "C" int gd_attn_sm100_config(int key, int value) {
     switch (key) {
         case 0: if (value < -1 || value > 4) break; g_np = value; return GD_OK;
         case 1: if (value != 0 && value != 4) break; g_poly = value; return GD_OK;
         case 2: if (value < 0 || value > 1) break; g_bwd_variant = value; return GD_OK;
         case 3: if (value < 0 || value > 4) break; g_bwd_np = value; return GD_OK;
-        case 4: if (value < 0 || value > 1) break; g_fwd_variant = value; return GD_OK;
     }
     return set_error(GD_ERR_INVALID, "gd_attn_sm100_config(key=%d, value=%d): see include/geodiffuser_b200.h", key, value);
 }

@@ -291,12 +291,12 @@ def _forward_impl(q, k, v, spec, proj=False):
     if M > 0:
         qk_st = _lib.host_longs([lay.q[0], lay.q[1], lay.kv[0], lay.kv[1]])
         a_b = torch.empty(h, N, ld, device=dev, dtype=torch.bfloat16)
-        call("gd_attn_probs", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), None, N, h, N, Nk, d, float(spec.scale), ptr(a_b), ld, qk_st, stream())
+        call("gd_attn_probs", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), None, N, h, N, Nk, d, float(spec.scale), ptr(a_b), ld, qk_st, stream(), tag=(h, N, Nk, d))
         a_e = torch.empty(h, M, ld, device=dev, dtype=torch.bfloat16)
-        call("gd_attn_probs", bp(q_e), bp(k_e), ptr(LSE[g_e]), ptr(cache.rows), M, h, N, Nk, d, float(spec.scale), ptr(a_e), ld, qk_st, stream())
+        call("gd_attn_probs", bp(q_e), bp(k_e), ptr(LSE[g_e]), ptr(cache.rows), M, h, N, Nk, d, float(spec.scale), ptr(a_e), ld, qk_st, stream(), tag=(h, M, Nk, d))
         n_tiles = (N + 63) // 64
         partial = torch.empty(h, n_tiles, M, 4, device=dev, dtype=torch.float32)
-        call("gd_corr_max_partial", ptr(a_e), ptr(a_b), h, M, N, Nk, ld, ptr(cache.m_inp), ptr(cache.m_bg), ptr(partial), stream())
+        call("gd_corr_max_partial", ptr(a_e), ptr(a_b), h, M, N, Nk, ld, ptr(cache.m_inp), ptr(cache.m_bg), ptr(partial), stream(), tag=(h, M, N, Nk))
         rem_terms = torch.empty(h * M, device=dev, dtype=torch.float32)
         g2 = torch.empty(h * M, 2, device=dev, dtype=torch.float32)
         j2 = torch.empty(h * M, 2, device=dev, dtype=torch.int32)
@@ -366,11 +366,11 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
         if _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024 and s["ld"] % 4 == 0:
             call("gd_attn_bwd_sm100", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
                  ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dq, ce0)), h, N, d, float(spec.scale), lay.strides(), dq_is_bf16,
-                 stream(), tag=(h, N, d))
+                 stream(), tag=(h, N, N, d))
         else:
             call("gd_attn_bwd", 0, bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
                  ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dq, ce0)), h, N, Nk, d, float(spec.scale), lay.strides(),
-                 dq_is_bf16, stream())
+                 dq_is_bf16, stream(), tag=(h, N, Nk, d))
         dk = None
         if spec.is_cross and spec.kind == "edit":
             dk = torch.zeros(k_shape, device=dev, dtype=k_dtype)
@@ -379,7 +379,7 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
             ws = torch.empty(splits, h, Nk, d, device=dev, dtype=torch.float32) if splits > 1 else None
             call("gd_attn_bwd_dk_split", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
                  ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dk, ce0)), ptr(ws), splits, h, N, Nk, d, float(spec.scale),
-                 lay.strides(out=lay.kv), int(k_dtype == torch.bfloat16), stream())
+                 lay.strides(out=lay.kv), int(k_dtype == torch.bfloat16), stream(), tag=(h, N, Nk, d))
         return dq, dk, None, None, None
 
 

@@ -74,6 +74,7 @@ class GraphedUNet:
         self.graph = None
         self.out = None
         self.path_launches = 0          # kernels of the C-ABI library inside the captured graph (re-counted on every replay)
+        self.path_flops = 0.0           # their algorithmic attention-path FLOP (_lib.FLOPS)
         self.after_eval = after_eval
         self.warmup_left = warmup
         self.pool = pool
@@ -94,14 +95,15 @@ class GraphedUNet:
                 self.warmup_left -= 1
                 return self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
             g = torch.cuda.CUDAGraph()
-            l0 = _lib.LAUNCHES
+            l0, f0 = _lib.LAUNCHES, _lib.FLOPS
             with _capture(g, self.pool, self.stream):
                 self.out = self._eval()
-            self.path_launches = _lib.LAUNCHES - l0
-            _lib.LAUNCHES = l0          # capturing launches nothing
+            self.path_launches, self.path_flops = _lib.LAUNCHES - l0, _lib.FLOPS - f0
+            _lib.LAUNCHES, _lib.FLOPS = l0, f0          # capturing launches nothing
             self.graph = g
         self.graph.replay()
         _lib.LAUNCHES += self.path_launches
+        _lib.FLOPS += self.path_flops
         return self.out
 
 
@@ -163,6 +165,7 @@ class GraphedGradPass:
         self.loss = self.g_lat = self.g_ctx = None
         self.num_layers = 0
         self.path_launches = 0
+        self.path_flops = 0.0
 
     def _run(self, c):
         with torch.enable_grad():
@@ -177,15 +180,17 @@ class GraphedGradPass:
         if self.graph is None:
             g = torch.cuda.CUDAGraph()
             step, layers = c.cur_step, c.loss_log_dict["num_layers"]
-            l0 = _lib.LAUNCHES
+            l0, f0 = _lib.LAUNCHES, _lib.FLOPS
             with _capture(g, _pool(self.model), _side_stream(self.model, latents.device), sync=self.sync):
                 self.loss, self.g_lat, self.g_ctx = self._run(c)
             self.path_launches, _lib.LAUNCHES = _lib.LAUNCHES - l0, l0
+            self.path_flops, _lib.FLOPS = _lib.FLOPS - f0, f0
             self.num_layers = c.loss_log_dict["num_layers"] - layers
             c.cur_step, c.loss_log_dict["num_layers"] = step, layers
             self.graph = g
         self.graph.replay()
         _lib.LAUNCHES += self.path_launches
+        _lib.FLOPS += self.path_flops
         c.loss = self.loss
         c.cur_step += 1
         c.loss_log_dict["num_layers"] += self.num_layers

@@ -87,7 +87,7 @@ int gd_attn_fwd_sm100(const void* const* q_host, const void* const* k_host, cons
  * score pairs of the online softmax evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (packed fp32x2 arithmetic;
  * default 2; -1 = round-1 scalar arithmetic with key 1 = every value-th exponential on the polynomial, value in {0, 4});
  * key 2: backward kernel, 0 = 128-key steps / one CTA per SM, 1 = 64-key steps / two CTAs per SM (default); key 3: polynomial share of
- * backward variant 1 (0..4 of 8 pairs, default 0); key 4: forward kernel, 0 = four softmax warps per CTA, 1 = eight (default). */
+ * backward variant 1 (0..4 of 8 pairs, default 0). */
 int gd_attn_sm100_config(int key, int value);
 
 /* ---- (3) backward, fused with the attention-map losses --------------------------------------------------------------- */

@@ -181,9 +181,10 @@ def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_ste
         rec["dq_absmax"] = np.float64(np.abs(gq.numpy()).max())
         if gk is not None:
             check("dk", g2k.numpy(), gk.numpy(), 1e-4)
-            rec["dk"] = gk.numpy()
-            if lk is not None:
-                rec["dk_loss"] = lk.numpy()
+            if not subsample:       # (self layers at the product shapes: dK belongs to the detached base sample, not stored)
+                rec["dk"] = gk.numpy()
+                if lk is not None:
+                    rec["dk_loss"] = lk.numpy()
         for key, val in c.loss_log_dict["cross" if is_cross else "self"].items():
             rec["term_" + key] = np.float64(float(val))
             check("term " + key, float(res["terms"][key]), float(val), 5e-5)

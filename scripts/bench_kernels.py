@@ -107,16 +107,14 @@ def bwd_case(H, N, d, M=0, sm100=False):
 cfg = lambda key, value: call("gd_attn_sm100_config", key, value)
 
 if only == "sweep":
-    for variant, nps in ((0, (2,)), (1, (0, 1, 2, 3))):
-        for np_ in nps:
-            cfg(4, variant)
-            cfg(0, np_)
-            print(f"--- fwd: {'four' if variant == 0 else 'eight'} softmax warps, packed arithmetic, {np_}/8 pairs on the polynomial", flush=True)
-            fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
-            fwd_case("gd_attn_fwd_sm100", 4, 8, 4096, 40)
-            fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
-            fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
-    cfg(4, 1)
+    for np_ in (-1, 0, 2, 3):
+        cfg(0, np_)
+        print(f"--- fwd: {'round-1 scalar arithmetic, poly=4' if np_ < 0 else f'packed arithmetic, {np_}/8 pairs on the polynomial'}", flush=True)
+        fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_sm100", 4, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
+        fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
+    cfg(0, 2)
     cfg(0, 2)
     for variant, nps in ((0, (0,)), (1, (1,))):
         for np_ in nps:

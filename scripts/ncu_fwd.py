@@ -8,8 +8,6 @@ np_ = int(sys.argv[1])
 G, N, d = (int(a) for a in sys.argv[2:5]) if len(sys.argv) > 4 else (3, 4096, 40)
 H = 8
 call("gd_attn_sm100_config", 0, np_)
-if len(sys.argv) > 5:
-    call("gd_attn_sm100_config", 4, int(sys.argv[5]))   # forward variant
 g = torch.Generator(device="cuda").manual_seed(1)
 mk = lambda: (torch.randn(H, N, d, device="cuda", generator=g) * 1.5).bfloat16()
 qs = [mk() for _ in range(G)]
