@@ -33,6 +33,9 @@ SIGNATURES = {
     "gd_cast_f32_to_bf16": [P, P, L, P],
     "gd_attn_probs": [P, P, P, P, I, I, I, I, I, F, P, I, P, P],
     "gd_corr_max_partial": [P, P, I, I, I, I, I, P, P, P, P],
+    "gd_removal_corr_sm100": [P, P, P, P, I, I, I, I, F, I, P, P, P, P, P],
+    "gd_attn_probs_rows2": [P, P, P, P, I, I, I, I, I, F, P, I, P, P],
+    "gd_removal_extra_rows": [P, P, I, I, I, I, P, P],
     "gd_attn_l1_losses": [P, P, P, P, P, P, P, F, F, F, F, F, I, I, I, P, P, I, P],
     "gd_removal_finalize": [P, I, I, I, I, P, P, P, F, P, P, I, I, I, P, P, P, P, P, P],
     "gd_loss_reduce": [P, I, P, I, P, P, P, F, P, P, P],
@@ -58,7 +61,7 @@ SIGNATURES = {
 _LIB = None
 HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
 LAUNCHES = 0  # CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
-KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 2, "gd_amodal_target": 2, "gd_attn_bwd_dk_split": 2,
+KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 1, "gd_amodal_target": 2, "gd_attn_bwd_dk_split": 2,
                     "gd_group_norm_nhwc_fwd": 1, "gd_group_norm_nhwc_bwd": 2, "gd_group_norm_nhwc_workspace": 0, "gd_group_norm_config": 0, "gd_masked_histogram_match": 3}  # every other entry point launches one
 
 

@@ -11,7 +11,7 @@ pids=""
 # geometry.cu, postprocess.cu: bit-exact artefacts behind a floating-point pipeline -> no FMA contraction
 $NVCC $COMMON -fmad=false -c geometry.cu -o _obj/geometry.o 2> _obj/geometry.log & pids="$pids $!"
 $NVCC $COMMON -fmad=false -c postprocess.cu -o _obj/postprocess.o 2> _obj/postprocess.log & pids="$pids $!"
-for f in attention_mma corr_gemm losses elementwise attention_sm100 body_norm; do
+for f in attention_mma corr_gemm losses elementwise attention_sm100 corr_sm100 body_norm; do
     if [ -f $f.cu ]; then
         $NVCC $COMMON -c $f.cu -o _obj/$f.o 2> _obj/$f.log & pids="$pids $!"
     fi

@@ -19,6 +19,7 @@ struct GemmParams {
     long a_hs, b_hs;            // head strides (elements)
     int lda, ldb;               // row strides (elements, multiple of 8)
     const int* a_rows;          // optional gather of A rows (M entries)
+    const int* a_rows2; int M2; // optional per-head gather: A row of output row m is a_rows2[(h * M2 + m % M2) * 2 + m / M2]  (M = 2 * M2)
     int H, M, N, K;
     // EPI_PROBS
     const float* lse; int lse_hs; float scale; bf16* p_out; long p_hs; int ldp;
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(GE_THREADS) gemm_nt_kernel(const GemmParams p)
             const int r = c / (GE_BK / 8), kk = (c % (GE_BK / 8)) * 8;
             const int m = m0 + r;
             const bool ok = (m < p.M) && (k0 + kk < p.K);
-            const long row = ok ? (p.a_rows ? p.a_rows[m] : m) : 0;
+            const long row = ok ? (p.a_rows2 ? p.a_rows2[((long)h * p.M2 + (m % p.M2)) * 2 + (m / p.M2)] : p.a_rows ? p.a_rows[m] : m) : 0;
             cp_async16(&As[st][r * GE_LD + kk], Ag + row * p.lda + (ok ? k0 + kk : 0), ok);
         }
         for (int c = tid; c < GE_BN * (GE_BK / 8); c += GE_THREADS) {
@@ -83,7 +84,7 @@ __global__ void __launch_bounds__(GE_THREADS) gemm_nt_kernel(const GemmParams p)
         for (int r = 0; r < 2; ++r) {
             const int m = m0 + rloc + r * 8;
             if (m >= p.M) continue;
-            const int qrow = p.a_rows ? p.a_rows[m] : m;
+            const int qrow = p.a_rows2 ? p.a_rows2[((long)h * p.M2 + (m % p.M2)) * 2 + (m / p.M2)] : p.a_rows ? p.a_rows[m] : m;
             const float l2 = p.lse[(long)h * p.lse_hs + qrow] * GE_LOG2E;
             bf16* out = p.p_out + (long)h * p.p_hs + (long)m * p.ldp;
 #pragma unroll
@@ -143,6 +144,24 @@ int gd_attn_probs(const void* q, const void* k, const float* lse, const int* row
     GD_CHECK_ARG((p.lda % 8) == 0 && (p.ldb % 8) == 0 && (p.a_hs % 8) == 0 && (p.b_hs % 8) == 0);
     p.H = H; p.M = M; p.N = Nk; p.K = d; p.lse = lse; p.lse_hs = N; p.scale = scale; p.p_out = (bf16*)p_out; p.p_hs = (long)M * ldp; p.ldp = ldp;
     dim3 grid(ceil_div(ldp, GE_BN), ceil_div(M, GE_BM), H);
+    gemm_nt_kernel<0><<<grid, GE_THREADS, 0, (cudaStream_t)stream>>>(p);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
+// The two base-map rows per (head, inpaint row) through which the removal loss back-propagates (attention_processors.py:256-266: the arg-max
+// positions j_bg, j_in of the masked correlation): P2[h, t * M + m, :] = softmax row of q[h, j2[(h * M + m) * 2 + t], :], bf16, row stride ldp.
+// Replaces the gather from a materialised base map.  j2: (H * M, 2) int32 as written by gd_removal_finalize.
+int gd_attn_probs_rows2(const void* q, const void* k, const float* lse, const int* j2, int M, int H, int N, int Nk, int d, float scale,
+                        void* p_out, int ldp, const long* qk_strides, void* stream) {
+    GD_CHECK_ARG(q && k && lse && j2 && p_out && H > 0 && N > 0 && Nk > 0 && M > 0 && d > 0 && (d % 8) == 0 && (ldp % 8) == 0 && ldp >= Nk);
+    GemmParams p = {};
+    p.a = (const bf16*)q; p.b = (const bf16*)k; p.a_rows2 = j2; p.M2 = M;
+    p.lda = qk_strides ? (int)qk_strides[0] : d; p.a_hs = qk_strides ? qk_strides[1] : (long)N * d;
+    p.ldb = qk_strides ? (int)qk_strides[2] : d; p.b_hs = qk_strides ? qk_strides[3] : (long)Nk * d;
+    GD_CHECK_ARG((p.lda % 8) == 0 && (p.ldb % 8) == 0 && (p.a_hs % 8) == 0 && (p.b_hs % 8) == 0);
+    p.H = H; p.M = 2 * M; p.N = Nk; p.K = d; p.lse = lse; p.lse_hs = N; p.scale = scale; p.p_out = (bf16*)p_out; p.p_hs = (long)2 * M * ldp; p.ldp = ldp;
+    dim3 grid(ceil_div(ldp, GE_BN), ceil_div(2 * M, GE_BM), H);
     gemm_nt_kernel<0><<<grid, GE_THREADS, 0, (cudaStream_t)stream>>>(p);
     GD_CHECK_LAUNCH();
     return GD_OK;

@@ -93,8 +93,9 @@ __global__ void removal_finalize_kernel(const float4* __restrict__ partial, int 
 }
 
 // extra[h, m, k] = g_bg * A_b[h, j_bg, k] + g_in * A_b[h, j_in, k]      (dL/dA_e rows, fp32)
+// (paired: the two rows of (h, m) are rows m and M + m of a_b -- gd_attn_probs_rows2's layout -- instead of rows j[hm])
 __global__ void removal_extra_kernel(const __nv_bfloat16* __restrict__ a_b, long ab_hs, int ld, int H, int M, int Nk,
-                                     const float2* __restrict__ g, const int2* __restrict__ j, float* __restrict__ extra) {
+                                     const float2* __restrict__ g, const int2* __restrict__ j, int paired, float* __restrict__ extra) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)H * M * ld) return;
     const int k = (int)(i % ld);
@@ -102,7 +103,7 @@ __global__ void removal_extra_kernel(const __nv_bfloat16* __restrict__ a_b, long
     const int h = (int)(hm / M);
     float v = 0.f;
     if (k < Nk) {
-        const float2 gg = g[hm]; const int2 jj = j[hm];
+        const float2 gg = g[hm]; const int2 jj = paired ? make_int2((int)(hm % M), M + (int)(hm % M)) : j[hm];
         const __nv_bfloat16* ab = a_b + (long)h * ab_hs;
         v = gg.x * __bfloat162float(ab[(long)jj.x * ld + k]) + gg.y * __bfloat162float(ab[(long)jj.y * ld + k]);
     }
@@ -232,13 +233,25 @@ int gd_attn_l1_losses(const float* e, const float* r, const float* t, const floa
 int gd_removal_finalize(const float* partial, int n_tiles, int H, int M, int S, const int* rows, const float* mask_in,
                         const float* mask_bg, float coef, const float* w_dev, const void* a_b, int Nb, int Nk, int ld, float* term, float* g2,
                         int* j2, float* delta_extra, float* extra, void* stream) {
-    GD_CHECK_ARG(partial && rows && mask_in && mask_bg && a_b && term && g2 && j2 && delta_extra && extra && H > 0 && M > 0 && n_tiles > 0);
+    GD_CHECK_ARG(partial && rows && mask_in && mask_bg && term && g2 && j2 && delta_extra && H > 0 && M > 0 && n_tiles > 0);
+    GD_CHECK_ARG(a_b == nullptr || extra != nullptr);
     cudaStream_t st = (cudaStream_t)stream;
     removal_finalize_kernel<<<ceil_div((long)H * M, 128), 128, 0, st>>>((const float4*)partial, n_tiles, H, M, S, rows, mask_in, mask_bg,
                                                                          coef, w_dev, term, (float2*)g2, (int2*)j2, delta_extra);
     GD_CHECK_LAUNCH();
-    removal_extra_kernel<<<ceil_div((long)H * M * ld, 256), 256, 0, st>>>((const __nv_bfloat16*)a_b, (long)Nb * ld, ld, H, M, Nk,
-                                                                           (const float2*)g2, (const int2*)j2, extra);
+    if (a_b) {      // base map materialised (cross layers / small levels): gather its two rows per (h, m); otherwise gd_removal_extra_rows follows
+        removal_extra_kernel<<<ceil_div((long)H * M * ld, 256), 256, 0, st>>>((const __nv_bfloat16*)a_b, (long)Nb * ld, ld, H, M, Nk,
+                                                                               (const float2*)g2, (const int2*)j2, 0, extra);
+        GD_CHECK_LAUNCH();
+    }
+    return GD_OK;
+}
+
+// extra[h, m, :] = g_bg * P2[h, m, :] + g_in * P2[h, M + m, :] with P2 from gd_attn_probs_rows2 (the two base-map rows recomputed, not gathered)
+int gd_removal_extra_rows(const void* p2, const float* g2, int H, int M, int Nk, int ld, float* extra, void* stream) {
+    GD_CHECK_ARG(p2 && g2 && extra && H > 0 && M > 0 && Nk > 0 && ld >= Nk);
+    removal_extra_kernel<<<ceil_div((long)H * M * ld, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)p2, (long)2 * M * ld, ld, H, M, Nk,
+                                                                                          (const float2*)g2, nullptr, 1, extra);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }

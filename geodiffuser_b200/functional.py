@@ -15,6 +15,7 @@ from . import _lib, geometry
 from ._lib import call, ptr, stream
 
 TERM_NAMES = ("sim", "movement", "removal", "smoothness", "amodal")
+CORR_SM100 = True   # removal-loss correlation of the self-attention levels on the tcgen05 kernel (False: materialised base map + mma.sync, for A/B tests)
 
 
 def gaussian_kernel5():
@@ -290,23 +291,40 @@ def _forward_impl(q, k, v, spec, proj=False):
     ld = (Nk + 7) // 8 * 8
     if M > 0:
         qk_st = _lib.host_longs([lay.q[0], lay.q[1], lay.kv[0], lay.kv[1]])
-        a_b = torch.empty(h, N, ld, device=dev, dtype=torch.bfloat16)
-        call("gd_attn_probs", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), None, N, h, N, Nk, d, float(spec.scale), ptr(a_b), ld, qk_st, stream(), tag=(h, N, Nk, d))
         a_e = torch.empty(h, M, ld, device=dev, dtype=torch.bfloat16)
         call("gd_attn_probs", bp(q_e), bp(k_e), ptr(LSE[g_e]), ptr(cache.rows), M, h, N, Nk, d, float(spec.scale), ptr(a_e), ld, qk_st, stream(), tag=(h, M, Nk, d))
-        n_tiles = (N + 63) // 64
-        partial = torch.empty(h, n_tiles, M, 4, device=dev, dtype=torch.float32)
-        call("gd_corr_max_partial", ptr(a_e), ptr(a_b), h, M, N, Nk, ld, ptr(cache.m_inp), ptr(cache.m_bg), ptr(partial), stream(), tag=(h, M, N, Nk))
         rem_terms = torch.empty(h * M, device=dev, dtype=torch.float32)
         g2 = torch.empty(h * M, 2, device=dev, dtype=torch.float32)
         j2 = torch.empty(h * M, 2, device=dev, dtype=torch.int32)
         delta_extra = torch.empty(h, M, device=dev, dtype=torch.float32)
         extra = torch.empty(h, M, ld, device=dev, dtype=torch.float32)
         wdev = spec.w_rem_dev
-        call("gd_removal_finalize", ptr(partial), n_tiles, h, M, S, ptr(cache.rows), ptr(cache.m_inp), ptr(cache.m_bg),
-             inv_rem if wdev is not None else w_rem * inv_rem, ptr(wdev), ptr(a_b), N, Nk, ld, ptr(rem_terms), ptr(g2), ptr(j2), ptr(delta_extra),
-             ptr(extra), stream())
-        del a_b, a_e, partial
+        coef = inv_rem if wdev is not None else w_rem * inv_rem
+        if CORR_SM100 and _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024:
+            # self-attention levels: the base map is never materialised -- its tiles are recomputed inside the tcgen05 correlation kernel
+            # from q_b, k_b and the stored LSE, and the two rows per (h, m) the backward needs are recomputed as softmax rows
+            n_tiles = N // 32
+            partial = torch.empty(h, n_tiles, M, 4, device=dev, dtype=torch.float32)
+            call("gd_removal_corr_sm100", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), ptr(a_e), h, M, N, d, float(spec.scale), ld, qk_st,
+                 ptr(cache.m_inp), ptr(cache.m_bg), ptr(partial), stream(), tag=(h, M, N, Nk))
+            call("gd_removal_finalize", ptr(partial), n_tiles, h, M, S, ptr(cache.rows), ptr(cache.m_inp), ptr(cache.m_bg), coef, ptr(wdev), None,
+                 N, Nk, ld, ptr(rem_terms), ptr(g2), ptr(j2), ptr(delta_extra), None, stream())
+            p2 = torch.empty(h, 2 * M, ld, device=dev, dtype=torch.bfloat16)
+            call("gd_attn_probs_rows2", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), ptr(j2), M, h, N, Nk, d, float(spec.scale), ptr(p2), ld,
+                 qk_st, stream())
+            call("gd_removal_extra_rows", ptr(p2), ptr(g2), h, M, Nk, ld, ptr(extra), stream())
+            del p2
+        else:
+            # cross layers (Nk = 77) and ragged shapes: materialise the base map (bf16, H x N x ld: 5 MB at Nk = 77) and correlate with mma.sync
+            a_b = torch.empty(h, N, ld, device=dev, dtype=torch.bfloat16)
+            call("gd_attn_probs", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), None, N, h, N, Nk, d, float(spec.scale), ptr(a_b), ld, qk_st, stream(), tag=(h, N, Nk, d))
+            n_tiles = (N + 63) // 64
+            partial = torch.empty(h, n_tiles, M, 4, device=dev, dtype=torch.float32)
+            call("gd_corr_max_partial", ptr(a_e), ptr(a_b), h, M, N, Nk, ld, ptr(cache.m_inp), ptr(cache.m_bg), ptr(partial), stream(), tag=(h, M, N, Nk))
+            call("gd_removal_finalize", ptr(partial), n_tiles, h, M, S, ptr(cache.rows), ptr(cache.m_inp), ptr(cache.m_bg), coef, ptr(wdev), ptr(a_b),
+                 N, Nk, ld, ptr(rem_terms), ptr(g2), ptr(j2), ptr(delta_extra), ptr(extra), stream())
+            del a_b
+        del a_e, partial
     terms = torch.empty(6, device=dev, dtype=torch.float32)
     call("gd_loss_reduce", ptr(partials), n_part, ptr(rem_terms), h * M if M > 0 else 0,
          _lib.host_f32([inv_sim, inv_mov, inv_amo, inv_smh, inv_smh, inv_rem]), _lib.host_f32([w_sim, w_mov, w_amo, w_sm, w_rem]),

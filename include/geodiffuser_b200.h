@@ -134,6 +134,20 @@ int gd_attn_probs(const void* q, const void* k, const float* lse, const int* row
 int gd_corr_max_partial(const void* a_e_bf16, const void* a_b_bf16, int H, int M, int Nb, int Nk, int ld, const float* mask_in,
                         const float* mask_bg, float* partial, void* stream);
 
+/* The same correlation + masked arg-max for the self-attention levels (N % 128 == 0, d in {40, 80}) as one tcgen05 / TMEM / TMA kernel that
+ * recomputes the base map A_b = softmax(scale q_b k_b^T) tile by tile from q_b, k_b (slabs, qk_strides_host as gd_attn_probs) and lse_b (H,N)
+ * instead of reading a materialised copy.  a_e (H, M, ld) bf16 from gd_attn_probs; partial (H, N/32, M, 4), one entry per block of 32 base rows. */
+int gd_removal_corr_sm100(const void* q_b, const void* k_b, const float* lse_b, const void* a_e_bf16, int H, int M, int N, int d, float scale,
+                          int ld, const long* qk_strides_host, const float* mask_in, const float* mask_bg, float* partial, void* stream);
+
+/* attention_processors.py:256-266, backward side: the two base-map rows per (head, inpaint row) at the arg-max positions j2 (H*M, 2) written by
+ * gd_removal_finalize, recomputed as softmax rows: p2 (H, 2M, ldp) bf16, rows [0,M) = j_bg, [M,2M) = j_in. */
+int gd_attn_probs_rows2(const void* q, const void* k, const float* lse, const int* j2, int M, int H, int N, int Nk, int d, float scale,
+                        void* p2_out, int ldp, const long* qk_strides_host, void* stream);
+
+/* extra[h, m, :] = g2[h*M+m].x * p2[h, m, :] + g2[h*M+m].y * p2[h, M+m, :]  (H, M, ld) fp32: dL/dA_e rows for gd_attn_bwd*. */
+int gd_removal_extra_rows(const void* p2_bf16, const float* g2, int H, int M, int Nk, int ld, float* extra, void* stream);
+
 /* attention_processors.py:231-246 (sim), 283-287 (movement), 289-305 (amodal, target t), loss.py:22-41 (smoothness): unweighted partial
  * sums (n_partials,5) and grad = d(weighted loss)/d replace_out.  c_* = weight / denominator of each term. */
 int gd_attn_l1_losses(const float* e, const float* r, const float* t, const float* m_bg, const float* m_edit, const float* m_am,
@@ -142,7 +156,8 @@ int gd_attn_l1_losses(const float* e, const float* r, const float* t, const floa
 
 /* attention_processors.py:259-266: distance weight, log terms, and the two non-zero gradient entries per row; extra (H,M,ld) and
  * delta_extra (H,M) feed gd_attn_bwd_prep / gd_attn_bwd.  coef = removal weight / (sum(mask_inpaint) * H + 1e-8); if w_dev (device scalar) is given, coef is
- * multiplied by *w_dev on the device: the adaptive schedule (optimization.py:7-105) changes that weight between passes of a captured graph. */
+ * multiplied by *w_dev on the device: the adaptive schedule (optimization.py:7-105) changes that weight between passes of a captured graph.
+ * a_b_bf16 == NULL: `extra` is not written here (gd_attn_probs_rows2 + gd_removal_extra_rows produce it without a materialised base map). */
 int gd_removal_finalize(const float* partial, int n_tiles, int H, int M, int S, const int* rows, const float* mask_in,
                         const float* mask_bg, float coef, const float* w_dev, const void* a_b_bf16, int Nb, int Nk, int ld, float* term,
                         float* g2, int* j2, float* delta_extra, float* extra, void* stream);

@@ -188,6 +188,21 @@ def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_ste
         for key, val in c.loss_log_dict["cross" if is_cross else "self"].items():
             rec["term_" + key] = np.float64(float(val))
             check("term " + key, float(res["terms"][key]), float(val), 5e-5)
+        if subsample:
+            # the SMOOTH part of the loss alone: only the removal term weighted (the L1 / TV terms have sign gradients, which no finite-precision
+            # evaluation reproduces element for element: tests judge them by the share of agreeing elements, and this part by the max norm)
+            c2 = make_ref_controller(R, kind, geo["mask"], geo)
+            c2.cur_step, c2.use_cfg, c2.coords_base, c2.coords_edit = cur_step, use_cfg, c.coords_base, c.coords_edit
+            w = {a: {k_: (float(v_) if k_ == "removal" else 0.0) for k_, v_ in c2.loss_weight_dict[a].items()} for a in ("self", "cross")}
+            c2.loss_weight_dict = w
+            c2.default_loss_weights = w
+            q3, k3, v3 = (a.detach().clone().requires_grad_(True) for a in (q, k, v))
+            c2(q3, k3, v3, is_cross, "down", transform_coords=tc, scale=scale, mask=None)
+            (rq,) = torch.autograd.grad(c2.loss, [q3])
+            rec["dq_removal"] = sub(rq.numpy())
+            rec["dq_removal_absmax"] = np.float64(np.abs(rq.numpy()).max())
+            rec["loss_removal_only"] = np.float64(float(c2.loss))
+            print(f"  removal-only loss {float(c2.loss):.6f}, |dq| max {np.abs(rq.numpy()).max():.3e}")
         if kind == "edit":
             rec["term_amodal"] = np.float64(float(res["terms"]["amodal"]))
     rec["meta"] = np.array([S, H, d, int(is_cross), int(use_cfg), seed, cur_step])
