@@ -151,15 +151,16 @@ def kernel_rooflines(dev, M64, M32, peaks, iters=60):
             delta = torch.randn(H, N, device=dev, generator=gen).float() * 0.01
             dq = torch.empty(H, N, d, device=dev, dtype=torch.float32)
             extra = rowmap = dl = None
+            Mp = (M + 3) // 4 * 4
             if M:
-                rows = torch.arange(N, device=dev)[(torch.arange(N, device=dev) // 64 % 3 == 1)][:M].int()      # clustered rows, like an object mask
+                rows = (torch.arange(M, device=dev) + N // 3).int()      # contiguous rows, like the inpaint set of an object mask
                 rowmap = torch.full((N,), -1, device=dev, dtype=torch.int32)
-                rowmap[rows.long()] = torch.arange(rows.numel(), device=dev, dtype=torch.int32)
-                extra = torch.randn(H, rows.numel(), ld, device=dev, generator=gen) * 0.01
+                rowmap[rows.long()] = torch.arange(M, device=dev, dtype=torch.int32)
+                extra = torch.randn(H, N, Mp, device=dev, generator=gen) * 0.01     # key-major (gd_removal_extra_rows key_major = 1)
                 dl = torch.ones(1, device=dev)
-            fns.append(lambda q=q, k=k, v=v, do=do, L=L, delta=delta, dq=dq, extra=extra, rowmap=rowmap, dl=dl, N=N, d=d, M=M, ld=ld:
-                       call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld,
-                            int(extra.shape[1]) if extra is not None else 0, ptr(dq), H, N, d, float(d ** -0.5), None, 0, stream()))
+            fns.append(lambda q=q, k=k, v=v, do=do, L=L, delta=delta, dq=dq, extra=extra, rowmap=rowmap, dl=dl, N=N, d=d, M=M, Mp=Mp, ld=ld:
+                       call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), Mp if M else ld,
+                            M, ptr(dq), H, N, d, float(d ** -0.5), None, 0, 1 if M else 0, stream()))
         ms = timed(fns)
         out.append(entry("gd_attn_bwd_sm100", f"attn_bwd64_sm100_kernel<{d}> H={H} N={N} removal rows M={M}", 6.0 * H * N * N * d, ms, operand_sets=nsets,
                          traffic=kernel_traffic(f"attn_bwd64_sm100_kernel<{d}> H={H} N={N}")))

@@ -309,7 +309,7 @@ constexpr int SM100_BWD_THREADS = 320;
 struct Sm100BwdMaps { CUtensorMap q, k, v, d_o; };
 struct Sm100BwdParams {
     const float* lse; const float* delta;
-    const float* extra; const float* extra_scale; const int* rowmap; int ex_ld, M;
+    const float* extra; const float* extra_scale; const int* rowmap; int ex_ld, M, ex_t;   // ex_t: extra is key-major (H, N, ex_ld)
     void* dq;                  // strided (dq_rs, dq_hs elements), fp32 or bf16
     long dq_rs, dq_hs;
     int dq_bf16;
@@ -317,235 +317,14 @@ struct Sm100BwdParams {
     float scale, scale2;
 };
 
-template <int D, int POLY>
-__global__ void __launch_bounds__(SM100_BWD_THREADS, 1)
-attn_bwd_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdParams p) {
-    constexpr int KB = (D + 63) / 64;
-    constexpr int KSTEPS = (D + 15) / 16;
-    constexpr int DV = KSTEPS * 16;
-    constexpr int TILE_BYTES = 128 * 128;
-    constexpr int OP_BYTES = KB * TILE_BYTES;
-    constexpr uint32_t COL_S = 0, COL_DP = 128, COL_DS = 256, COL_DQ = 320;
-    constexpr int TMEM_COLS = 512;
-    constexpr int NSTAGE = 2;                       // V ring (a V tile is free again once S/dP(j) are complete)
-    constexpr int KSTAGE = (D <= 64) ? 4 : 3;       // K ring: a K tile is needed at both ends of its step (scores, then dQ), so it is deeper
-    constexpr int NEW = 8;                          // elementwise warps
-    constexpr int NC = BN / 2;                      // key columns per elementwise thread
-
-    extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sQ = smem;
-    unsigned char* sDO = sQ + OP_BYTES;
-    unsigned char* sK = sDO + OP_BYTES;
-    unsigned char* sV = sK + KSTAGE * OP_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTAGE * OP_BYTES);
-    uint64_t* q_full = bars + 0;
-    uint64_t* v_full = bars + 1;    // [2]
-    uint64_t* v_empty = bars + 3;   // [2]
-    uint64_t* s_full = bars + 5;    // S(j) and dP(j) complete
-    uint64_t* s_free = bars + 6;    // both in registers (8 arrivals)
-    uint64_t* ds_full = bars + 7;   // dS(j) stored (8 arrivals)
-    uint64_t* dq_done = bars + 8;   // dQ += dS(j) K(j) complete
-    uint64_t* k_full = bars + 9;    // [KSTAGE]
-    uint64_t* k_empty = bars + 9 + KSTAGE;   // [KSTAGE]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9 + 2 * KSTAGE);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.y, q0 = blockIdx.x * BM;
-    const int N = p.N;
-    const int nT = N / BN;
-
-    if (threadIdx.x == 0) {
-        mbar_init(q_full, 1);
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
-        for (int s = 0; s < KSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); }
-        mbar_init(s_full, 1); mbar_init(s_free, NEW); mbar_init(ds_full, NEW); mbar_init(dq_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    if (warp == NEW + 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp == NEW && lane == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.v); tma_prefetch_desc(&maps.d_o); }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
-
-    if (warp == NEW) {
-        // ================= TMA producer =================
-        if (lane == 0) {
-            mbar_expect_tx(q_full, 2 * OP_BYTES);
-#pragma unroll
-            for (int b = 0; b < KB; ++b) {
-                tma_load_3d(sQ + b * TILE_BYTES, &maps.q, q_full, b * 64, q0, h);
-                tma_load_3d(sDO + b * TILE_BYTES, &maps.d_o, q_full, b * 64, q0, h);
-            }
-            for (int j = 0; j < nT; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                const int ks = j % KSTAGE;
-                const uint32_t kph = (j / KSTAGE) & 1;
-                mbar_wait_relaxed(k_empty + ks, kph ^ 1);
-                mbar_expect_tx(k_full + ks, OP_BYTES);
-#pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_3d(sK + ks * OP_BYTES + b * TILE_BYTES, &maps.k, k_full + ks, b * 64, j * BN, h);
-                mbar_wait_relaxed(v_empty + s, ph ^ 1);
-                mbar_expect_tx(v_full + s, OP_BYTES);
-#pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v, v_full + s, b * 64, j * BN, h);
-            }
-        }
-    } else if (warp == NEW + 1) {
-        // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t IDESC_SS = make_idesc(BM, BN, 0, 0);
-            constexpr uint32_t IDESC_DQ = make_idesc(BM, DV, 0, 1);
-            const uint32_t aQ = smem_addr(sQ), aDO = smem_addr(sDO);
-            auto issue_scores = [&](int j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                const int kst = j % KSTAGE;
-                mbar_wait(k_full + kst, (j / KSTAGE) & 1);
-                mbar_wait(v_full + s, ph);
-                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
-                tc_fence_after();
-                const uint32_t aK = smem_addr(sK + kst * OP_BYTES), aV = smem_addr(sV + s * OP_BYTES);
-#pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tmem + COL_S, make_desc(aQ + off, 16, 1024), make_desc(aK + off, 16, 1024), IDESC_SS, ks > 0);
-                }
-#pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;
-                    umma_ss(tmem + COL_DP, make_desc(aDO + off, 16, 1024), make_desc(aV + off, 16, 1024), IDESC_SS, ks > 0);
-                }
-                tc_commit(s_full);        // S(j), dP(j) complete
-                tc_commit(v_empty + s);   // V stage reusable (K is still needed by the dQ product)
-            };
-            mbar_wait(q_full, 0);
-            issue_scores(0);
-            for (int j = 0; j < nT; ++j) {
-                if (j + 1 < nT) issue_scores(j + 1);
-                const int s = j % KSTAGE;
-                mbar_wait(ds_full, j & 1);
-                tc_fence_after();
-                const uint32_t aK = smem_addr(sK + s * OP_BYTES);
-#pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk)
-                    umma_ts(tmem + COL_DQ, tmem + COL_DS + kk * 8, make_desc(aK + kk * 2048, TILE_BYTES, 1024), IDESC_DQ, (j > 0 || kk > 0));
-                tc_commit(dq_done);
-                tc_commit(k_empty + s);
-            }
-        }
-    } else {
-        // ================= elementwise warps 0-7 =================
-        const int quarter = warp & 3, half = warp >> 2;
-        const int rloc = quarter * 32 + lane;
-        const int row = q0 + rloc;
-        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        const float scale2 = p.scale2;
-        const float lse2 = p.lse[(long)h * N + row] * 1.4426950408889634f;
-        const float delta = p.delta[(long)h * N + row];
-        const int slot = p.rowmap ? p.rowmap[row] : -1;
-        const float ex_scale = (p.extra && p.extra_scale) ? *p.extra_scale : 1.0f;
-        const float* exrow = (slot >= 0) ? p.extra + ((long)h * p.M + slot) * p.ex_ld : nullptr;
-        for (int j = 0; j < nT; ++j) {
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            uint32_t sr[NC], dp[NC];
-#pragma unroll
-            for (int c = 0; c < NC / 32; ++c) {
-                tmem_ld32(tmem + lane_off + COL_S + half * NC + c * 32, sr + c * 32);
-                tmem_ld32(tmem + lane_off + COL_DP + half * NC + c * 32, dp + c * 32);
-            }
-            tmem_wait_ld();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(s_free);
-            if (exrow) {                                      // removal-loss rows: dL/dP of this row joins dP
-                const float* e4 = exrow + j * BN + half * NC;
-#pragma unroll
-                for (int c = 0; c < NC; c += 4) {
-                    const float4 v = *reinterpret_cast<const float4*>(e4 + c);
-                    dp[c] = __float_as_uint(fmaf(ex_scale, v.x, __uint_as_float(dp[c])));
-                    dp[c + 1] = __float_as_uint(fmaf(ex_scale, v.y, __uint_as_float(dp[c + 1])));
-                    dp[c + 2] = __float_as_uint(fmaf(ex_scale, v.z, __uint_as_float(dp[c + 2])));
-                    dp[c + 3] = __float_as_uint(fmaf(ex_scale, v.w, __uint_as_float(dp[c + 3])));
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < NC / 32; ++cc) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const int e = cc * 32 + 2 * c;
-                    const float x0 = fmaf(__uint_as_float(sr[e]), scale2, -lse2);
-                    const float x1 = fmaf(__uint_as_float(sr[e + 1]), scale2, -lse2);
-                    const float p0 = use_poly<POLY>(e) ? ex2_poly(x0) : ex2(x0);
-                    const float p1 = use_poly<POLY>(e + 1) ? ex2_poly(x1) : ex2(x1);
-                    const float d0 = p0 * (__uint_as_float(dp[e]) - delta);
-                    const float d1 = p1 * (__uint_as_float(dp[e + 1]) - delta);
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
-                    pk[c] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-                if (cc == 0 && j > 0) {
-                    mbar_wait(dq_done, (j - 1) & 1);          // dS(j-1) has been consumed
-                    tc_fence_after();
-                }
-                tmem_st16(tmem + lane_off + COL_DS + (half * NC + cc * 32) / 2, pk);
-            }
-            tmem_wait_st();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(ds_full);
-        }
-        // epilogue: dQ * scale -> global fp32; the two warps of a quarter split the 16-column chunks
-        mbar_wait(dq_done, (nT - 1) & 1);
-        tc_fence_after();
-        unsigned char* og = reinterpret_cast<unsigned char*>(p.dq) + ((long)h * p.dq_hs + (long)row * p.dq_rs) * (p.dq_bf16 ? 2 : 4);
-        const float sc = p.scale;
-#pragma unroll
-        for (int c = 0; c < DV / 16; ++c) {
-            if ((c & 1) != half) continue;
-            uint32_t orr[16];
-            tmem_ld16(tmem + lane_off + COL_DQ + c * 16, orr);
-            tmem_wait_ld();
-            float f[16];
-#pragma unroll
-            for (int e = 0; e < 16; ++e) f[e] = __uint_as_float(orr[e]) * sc;
-            if (p.dq_bf16) {
-#pragma unroll
-                for (int e = 0; e < 16; e += 8)
-                    if (c * 16 + e < D) {
-                        uint4 v;
-                        __nv_bfloat162 b0 = __floats2bfloat162_rn(f[e], f[e + 1]), b1 = __floats2bfloat162_rn(f[e + 2], f[e + 3]);
-                        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[e + 4], f[e + 5]), b3 = __floats2bfloat162_rn(f[e + 6], f[e + 7]);
-                        v.x = *reinterpret_cast<uint32_t*>(&b0); v.y = *reinterpret_cast<uint32_t*>(&b1);
-                        v.z = *reinterpret_cast<uint32_t*>(&b2); v.w = *reinterpret_cast<uint32_t*>(&b3);
-                        *reinterpret_cast<uint4*>(og + (c * 16 + e) * 2) = v;
-                    }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 16; e += 4)
-                    if (c * 16 + e < D) *reinterpret_cast<float4*>(og + (c * 16 + e) * 4) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == NEW + 1) {
-        tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------------------------
-// Backward, second form (the product path): same mathematics and operands as attn_bwd_sm100_kernel, re-tiled so that TWO CTAs share an SM.
+// The kernel: one CTA per (head, 128-query tile), ten warps (0-7 elementwise: lane quarter x key half, 8 = TMA, 9 = MMA issuer), TWO CTAs per SM.
 // 64-key steps: TMEM per CTA = S 64 + dP 64 + dS 32 + dQ <= 80 = 240 -> 256 columns; shared memory at head_dim 40 = Q 16 K + dO 16 K +
-// K ring 4 x 8 K + V ring 2 x 8 K = 80 KB.  The first form ran one CTA per SM: its two elementwise warps per sub-partition could not cover the
-// MUFU latency (50 % XU, 38 % issue, 2188 clk per 128-key step against 1024 clk of exponentials) and 256 CTAs on 148 SMs ran as two
-// waves; here 16 elementwise warps per SM are resident, all 256 CTAs of a 64^2 layer are co-resident (296 slots), and the per-score
-// arithmetic is packed (FFMA2 / FADD2 / FMUL2): 3 issue slots per score instead of 4.5.
+// K ring 4 x 8 K + V ring 2 x 8 K = 80 KB.  S and dP are released as soon as they sit in registers, so the two score GEMMs of step j+1 run
+// under step j's exponentials; a K tile is needed at both ends of its step (scores, then dQ), hence its deeper ring.  (Round 1 ran 128-key
+// steps with one CTA per SM: same speed without removal rows -- 75 us at H=8, N=4096 -- but 256 CTAs on 148 SMs ran as two waves and the
+// CTAs that own removal-loss rows set the makespan: 118 us against 85 us here; history in git.)  Per-score arithmetic is packed
+// (FFMA2 / FADD2 / FMUL2): 3 issue slots per score.
 template <int D, int NP>
 __global__ void __launch_bounds__(SM100_BWD_THREADS, 2)
 attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100BwdParams p) {
@@ -677,15 +456,26 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
         const u64 sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-lse2, -lse2), nd2 = pk2(-delta, -delta);
         const int slot = p.rowmap ? p.rowmap[row] : -1;
         const float ex_scale = (p.extra && p.extra_scale) ? *p.extra_scale : 1.0f;
-        const float* exrow = (slot >= 0) ? p.extra + ((long)h * p.M + slot) * p.ex_ld + half * NC : nullptr;
+        // this thread's removal-loss row: row-major extra (H, M, ex_ld): 32 consecutive floats per step; key-major (H, N, ex_ld): one float per
+        // key, ex_ld apart, consecutive slots (= consecutive lanes) adjacent in memory
+        const long ex_ks = p.ex_t ? p.ex_ld : 1;
+        const float* exrow = (slot >= 0) ? (p.ex_t ? p.extra + ((long)h * N + half * NC) * p.ex_ld + slot
+                                                   : p.extra + ((long)h * p.M + slot) * p.ex_ld + half * NC) : nullptr;
         const bool any_ex = __any_sync(0xffffffffu, exrow != nullptr);   // warp-uniform: does this warp own removal-loss rows at all
         for (int j = 0; j < nT; ++j) {
             // removal-loss rows: this step's 32 floats of dL/dP are requested BEFORE the wait for the score GEMMs, so that their L2 latency
             // runs under it (round 1 loaded them inside the arithmetic: the few CTAs that own inpaint rows then set the kernel's makespan)
             float4 ev[NC / 4];
             if (any_ex && exrow) {
+                if (p.ex_t) {
+                    const float* e0 = exrow + (long)j * BNK * ex_ks;
 #pragma unroll
-                for (int i = 0; i < NC / 4; ++i) ev[i] = *reinterpret_cast<const float4*>(exrow + j * BNK + 4 * i);
+                    for (int i = 0; i < NC / 4; ++i)
+                        ev[i] = make_float4(__ldg(e0 + (4 * i) * ex_ks), __ldg(e0 + (4 * i + 1) * ex_ks), __ldg(e0 + (4 * i + 2) * ex_ks), __ldg(e0 + (4 * i + 3) * ex_ks));
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NC / 4; ++i) ev[i] = *reinterpret_cast<const float4*>(exrow + j * BNK + 4 * i);
+                }
             }
             mbar_wait(s_full, j & 1);
             tc_fence_after();
@@ -781,7 +571,7 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
 static int g_poly = 4;   // round-1 arithmetic only (g_np < 0): every g_poly-th exponential goes to the FMA pipe
-static int g_bwd_variant = 1, g_bwd_np = 0;
+static int g_bwd_np = 0;
 static int g_np = 2;     // tuning knob (gd_attn_sm100_config): packed arithmetic, g_np of every 8 score pairs on the FMA-pipe polynomial
 
 template <int D, int POLY, int NP> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
@@ -812,22 +602,6 @@ template <int D> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Par
         case 4: return launch_sm100<D, 4, -1>(maps, p, G, st);
     }
     return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for poly=%d np=%d", g_poly, g_np);
-}
-
-template <int D, int POLY> static int launch_bwd_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
-    constexpr int KB = (D + 63) / 64;
-    constexpr int KSTAGE = (D <= 64) ? 4 : 3;
-    const size_t smem = (size_t)(4 + KSTAGE) * KB * 128 * 128 + 256 + 1024;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_bwd_sm100_kernel<D, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        configured = true;
-    }
-    dim3 grid(p.N / BM, p.H, 1);
-    attn_bwd_sm100_kernel<D, POLY><<<grid, SM100_BWD_THREADS, smem, st>>>(maps, p);
-    GD_CHECK_LAUNCH();
-    return GD_OK;
 }
 
 template <int D, int NP> static int launch_bwd64_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
@@ -891,13 +665,11 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
 //   key 0  fwd: packed fp32x2 softmax arithmetic with `value` in 0..4 of every 8 score pairs on the FMA-pipe polynomial (default 2);
 //               value -1 selects the round-1 scalar arithmetic (A/B measurements), whose polynomial share is key 1
 //   key 1  fwd, scalar arithmetic only: every value-th exponential on the polynomial, value in {0, 4}
-//   key 2  bwd: 0 = round-1 kernel (128-key steps, one CTA per SM), 1 = 64-key steps, two CTAs per SM, packed arithmetic (default)
-//   key 3  bwd variant 1: value in 0..4 of every 8 score pairs on the polynomial (default 0)
+//   key 3  bwd: value in 0..4 of every 8 score pairs on the polynomial (default 0)
 extern "C" int gd_attn_sm100_config(int key, int value) {
     switch (key) {
         case 0: if (value < -1 || value > 4) break; g_np = value; return GD_OK;
         case 1: if (value != 0 && value != 4) break; g_poly = value; return GD_OK;
-        case 2: if (value < 0 || value > 1) break; g_bwd_variant = value; return GD_OK;
         case 3: if (value < 0 || value > 4) break; g_bwd_np = value; return GD_OK;
     }
     return set_error(GD_ERR_INVALID, "gd_attn_sm100_config(key=%d, value=%d): see include/geodiffuser_b200.h", key, value);
@@ -906,30 +678,27 @@ extern "C" int gd_attn_sm100_config(int key, int value) {
 // dQ of softmax(scale q k^T) v for the self-attention levels (N == Nk, N % 128 == 0, d in {40, 80}); same operands as gd_attn_bwd mode 0.
 extern "C" int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
                                  const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* dq, int H, int N,
-                                 int d, float scale, const long* strides, int dq_is_bf16, void* stream) {
+                                 int d, float scale, const long* strides, int dq_is_bf16, int extra_key_major, void* stream) {
     GD_CHECK_ARG(q && k && v && d_o && lse && delta && dq && H > 0);
     GD_CHECK_ARG((extra == nullptr) == (rowmap == nullptr));
     if (!(N % 128 == 0 && (d == 40 || d == 80)))
         return set_error(GD_ERR_UNSUPPORTED, "gd_attn_bwd_sm100 serves N %% 128 == 0, d in {40, 80}; got N=%d d=%d", N, d);
-    if (extra && (ex_ld % 4 != 0 || ex_ld < N)) return set_error(GD_ERR_INVALID, "gd_attn_bwd_sm100: extra row stride %d must be >= N and a multiple of 4", ex_ld);
+    if (extra && !extra_key_major && (ex_ld % 4 != 0 || ex_ld < N))
+        return set_error(GD_ERR_INVALID, "gd_attn_bwd_sm100: extra row stride %d must be >= N and a multiple of 4", ex_ld);
+    if (extra && extra_key_major && ex_ld < M) return set_error(GD_ERR_INVALID, "gd_attn_bwd_sm100: key-major extra needs ex_ld >= M (%d < %d)", ex_ld, M);
     const long q_rs = strides ? strides[0] : d, q_hs = strides ? strides[1] : (long)N * d;
     const long kv_rs = strides ? strides[2] : d, kv_hs = strides ? strides[3] : (long)N * d;
     Sm100BwdMaps maps;
     int rc;
     if ((rc = make_map(&maps.q, q, N, H, d, q_rs, q_hs, BM)) != GD_OK) return rc;
     if ((rc = make_map(&maps.d_o, d_o, N, H, d, d, (long)N * d, BM)) != GD_OK) return rc;
-    const int key_rows = g_bwd_variant == 1 ? 64 : BN;      // keys per step of the selected kernel = TMA box rows of K / V
-    if ((rc = make_map(&maps.k, k, N, H, d, kv_rs, kv_hs, key_rows)) != GD_OK) return rc;
-    if ((rc = make_map(&maps.v, v, N, H, d, kv_rs, kv_hs, key_rows)) != GD_OK) return rc;
+    if ((rc = make_map(&maps.k, k, N, H, d, kv_rs, kv_hs, 64)) != GD_OK) return rc;      // 64-key steps = TMA box rows of K / V
+    if ((rc = make_map(&maps.v, v, N, H, d, kv_rs, kv_hs, 64)) != GD_OK) return rc;
     Sm100BwdParams p;
-    p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.dq = dq;
+    p.lse = lse; p.delta = delta; p.extra = extra; p.extra_scale = extra_scale; p.rowmap = rowmap; p.ex_ld = ex_ld; p.M = M; p.ex_t = extra_key_major; p.dq = dq;
     p.dq_rs = strides ? strides[4] : d; p.dq_hs = strides ? strides[5] : (long)N * d; p.dq_bf16 = dq_is_bf16;
     if ((p.dq_rs % 8) != 0 || (p.dq_hs % 8) != 0) return set_error(GD_ERR_INVALID, "gd_attn_bwd_sm100: dq strides must be multiples of 8");
     p.H = H; p.N = N; p.scale = scale; p.scale2 = scale * 1.4426950408889634f;
     cudaStream_t st = (cudaStream_t)stream;
-    // all exponentials on the MUFU: with ~4.5 instructions per score the elementwise warps are issue-bound, the polynomial only adds to that
-    // (measured: 110.9 us vs 124.6 us at H=8, N=4096, d=40)
-    if (g_bwd_variant == 1) return d == 40 ? dispatch_bwd64_sm100<40>(maps, p, st) : dispatch_bwd64_sm100<80>(maps, p, st);
-    if (d == 40) return launch_bwd_sm100<40, 0>(maps, p, st);
-    return launch_bwd_sm100<80, 0>(maps, p, st);
+    return d == 40 ? dispatch_bwd64_sm100<40>(maps, p, st) : dispatch_bwd64_sm100<80>(maps, p, st);
 }

@@ -110,6 +110,32 @@ __global__ void removal_extra_kernel(const __nv_bfloat16* __restrict__ a_b, long
     extra[i] = v;
 }
 
+// The same rows, key-major: extraT[h, k, m] = g_bg * P2[h, m, k] + g_in * P2[h, M + m, k]   (H, Nk, Mp) fp32, Mp = M rounded up to 4.
+// The tcgen05 backward's threads own one query row each and walk the keys: with the inpaint rows contiguous along m, the 32 lanes of a warp
+// (consecutive query rows -> consecutive slots m) read consecutive floats for a given key -- one or two 128-byte lines per load instead of 32.
+// 32 x 32 tiles through shared memory so that both the P2 reads (along k) and the extraT writes (along m) are coalesced.
+__global__ void __launch_bounds__(256) removal_extra_t_kernel(const __nv_bfloat16* __restrict__ p2, int ld, int H, int M, int Mp, int Nk,
+                                                              const float2* __restrict__ g, float* __restrict__ extra_t) {
+    __shared__ float tile[32][33];
+    const int h = blockIdx.z, m0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const __nv_bfloat16* base = p2 + (long)h * 2 * M * ld;
+    for (int r = ty; r < 32; r += 8) {
+        const int m = m0 + r, k = k0 + tx;
+        float v = 0.f;
+        if (m < M && k < Nk) {
+            const float2 gg = g[(long)h * M + m];
+            v = gg.x * __bfloat162float(base[(long)m * ld + k]) + gg.y * __bfloat162float(base[(long)(M + m) * ld + k]);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int k = k0 + r, m = m0 + tx;
+        if (k < Nk && m < Mp) extra_t[((long)h * Nk + k) * Mp + m] = tile[tx][r];
+    }
+}
+
 // terms[0..5] = sim, movement, removal, smoothness, amodal, total(weighted); single block, fixed summation order.
 // terms_accum (optional, 6 floats) += terms  -- the controller's running per-step log / loss.
 struct LossReduceParams {
@@ -248,8 +274,15 @@ int gd_removal_finalize(const float* partial, int n_tiles, int H, int M, int S, 
 }
 
 // extra[h, m, :] = g_bg * P2[h, m, :] + g_in * P2[h, M + m, :] with P2 from gd_attn_probs_rows2 (the two base-map rows recomputed, not gathered)
-int gd_removal_extra_rows(const void* p2, const float* g2, int H, int M, int Nk, int ld, float* extra, void* stream) {
+int gd_removal_extra_rows(const void* p2, const float* g2, int H, int M, int Nk, int ld, float* extra, int key_major, void* stream) {
     GD_CHECK_ARG(p2 && g2 && extra && H > 0 && M > 0 && Nk > 0 && ld >= Nk);
+    if (key_major) {        // extra (H, Nk, Mp), Mp = M rounded up to 4: the layout gd_attn_bwd_sm100 reads with extra_key_major = 1
+        const int Mp = (M + 3) / 4 * 4;
+        dim3 grid(ceil_div(Nk, 32), ceil_div(Mp, 32), H);
+        removal_extra_t_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)p2, ld, H, M, Mp, Nk, (const float2*)g2, extra);
+        GD_CHECK_LAUNCH();
+        return GD_OK;
+    }
     removal_extra_kernel<<<ceil_div((long)H * M * ld, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)p2, (long)2 * M * ld, ld, H, M, Nk,
                                                                                           (const float2*)g2, nullptr, 1, extra);
     GD_CHECK_LAUNCH();

@@ -297,7 +297,6 @@ def _forward_impl(q, k, v, spec, proj=False):
         g2 = torch.empty(h * M, 2, device=dev, dtype=torch.float32)
         j2 = torch.empty(h * M, 2, device=dev, dtype=torch.int32)
         delta_extra = torch.empty(h, M, device=dev, dtype=torch.float32)
-        extra = torch.empty(h, M, ld, device=dev, dtype=torch.float32)
         wdev = spec.w_rem_dev
         coef = inv_rem if wdev is not None else w_rem * inv_rem
         if CORR_SM100 and _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024:
@@ -312,10 +311,15 @@ def _forward_impl(q, k, v, spec, proj=False):
             p2 = torch.empty(h, 2 * M, ld, device=dev, dtype=torch.bfloat16)
             call("gd_attn_probs_rows2", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), ptr(j2), M, h, N, Nk, d, float(spec.scale), ptr(p2), ld,
                  qk_st, stream())
-            call("gd_removal_extra_rows", ptr(p2), ptr(g2), h, M, Nk, ld, ptr(extra), stream())
+            # dL/dA_e rows, key-major (H, Nk, Mp): the layout the tcgen05 backward reads coalesced
+            ex_key_major, ex_ld = 1, (M + 3) // 4 * 4
+            extra = torch.empty(h, Nk, ex_ld, device=dev, dtype=torch.float32)
+            call("gd_removal_extra_rows", ptr(p2), ptr(g2), h, M, Nk, ld, ptr(extra), 1, stream())
             del p2
         else:
             # cross layers (Nk = 77) and ragged shapes: materialise the base map (bf16, H x N x ld: 5 MB at Nk = 77) and correlate with mma.sync
+            ex_key_major, ex_ld = 0, ld
+            extra = torch.empty(h, M, ld, device=dev, dtype=torch.float32)
             a_b = torch.empty(h, N, ld, device=dev, dtype=torch.bfloat16)
             call("gd_attn_probs", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), None, N, h, N, Nk, d, float(spec.scale), ptr(a_b), ld, qk_st, stream(), tag=(h, N, Nk, d))
             n_tiles = (N + 63) // 64
@@ -330,6 +334,8 @@ def _forward_impl(q, k, v, spec, proj=False):
          _lib.host_f32([inv_sim, inv_mov, inv_amo, inv_smh, inv_smh, inv_rem]), _lib.host_f32([w_sim, w_mov, w_amo, w_sm, w_rem]),
          ptr(spec.w_rem_dev), 1.0 if use_amodal else 0.0, ptr(terms), ptr(spec.log_accum), stream())
     saved.update(g_loss=g_loss, extra=extra, delta_extra=delta_extra, M=M)
+    if M > 0:
+        saved.update(ex_ld=ex_ld, ex_key_major=ex_key_major)
     return out, terms, saved
 
 
@@ -381,13 +387,15 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
              h, N, d, ptr(d_o), ptr(delta), stream())
         # dQ of the edit entry is written by the kernel straight into its slab of the full gradient tensor, in q's layout and dtype
         dq_is_bf16 = int(q_dtype == torch.bfloat16)
+        ex_ld, ex_km = (s["ex_ld"], s["ex_key_major"]) if has_extra else (s["ld"], 0)
         if _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024 and s["ld"] % 4 == 0:
             call("gd_attn_bwd_sm100", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dq, ce0)), h, N, d, float(spec.scale), lay.strides(), dq_is_bf16,
-                 stream(), tag=(h, N, N, d))
+                 ptr(d_loss) if has_extra else None, rowmap, ex_ld, M, bp(lay.sl(dq, ce0)), h, N, d, float(spec.scale), lay.strides(), dq_is_bf16,
+                 ex_km, stream(), tag=(h, N, N, d))
         else:
+            assert ex_km == 0
             call("gd_attn_bwd", 0, bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-                 ptr(d_loss) if has_extra else None, rowmap, s["ld"], M, bp(lay.sl(dq, ce0)), h, N, Nk, d, float(spec.scale), lay.strides(),
+                 ptr(d_loss) if has_extra else None, rowmap, ex_ld, M, bp(lay.sl(dq, ce0)), h, N, Nk, d, float(spec.scale), lay.strides(),
                  dq_is_bf16, stream(), tag=(h, N, Nk, d))
         dk = None
         if spec.is_cross and spec.kind == "edit":

@@ -86,8 +86,7 @@ int gd_attn_fwd_sm100(const void* const* q_host, const void* const* k_host, cons
 /* Tuning knobs of the tcgen05 kernels (process-wide, not part of the reference surface).  key 0: forward, `value` in 0..4 of every 8
  * score pairs of the online softmax evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (packed fp32x2 arithmetic;
  * default 2; -1 = round-1 scalar arithmetic with key 1 = every value-th exponential on the polynomial, value in {0, 4});
- * key 2: backward kernel, 0 = 128-key steps / one CTA per SM, 1 = 64-key steps / two CTAs per SM (default); key 3: polynomial share of
- * backward variant 1 (0..4 of 8 pairs, default 0). */
+ * key 3: polynomial share of the backward kernel (0..4 of 8 pairs, default 0). */
 int gd_attn_sm100_config(int key, int value);
 
 /* ---- (3) backward, fused with the attention-map losses --------------------------------------------------------------- */
@@ -115,10 +114,11 @@ int gd_attn_bwd_dk_split(const void* q, const void* k, const void* v, const void
                          int splits, int H, int N, int Nk, int d, float scale, const long* strides_host, int out_is_bf16, void* stream);
 
 /* Same operands and result as gd_attn_bwd mode 0 (dQ), tcgen05 / TMEM / TMA kernel for the self-attention levels:
- * N == Nk, N % 128 == 0, d in {40, 80}; extra rows (if any) 16-byte aligned (ex_ld % 4 == 0). */
+ * N == Nk, N % 128 == 0, d in {40, 80}.  extra_key_major = 0: extra (H, M, ex_ld) as for gd_attn_bwd (ex_ld % 4 == 0);
+ * extra_key_major = 1: extra (H, N, ex_ld) with ex_ld = M rounded up to 4 (gd_removal_extra_rows key_major = 1). */
 int gd_attn_bwd_sm100(const void* q, const void* k, const void* v, const void* d_o, const float* lse, const float* delta,
                       const float* extra, const float* extra_scale, const int* rowmap, int ex_ld, int M, void* dq, int H, int N,
-                      int d, float scale, const long* strides_host, int dq_is_bf16, void* stream);
+                      int d, float scale, const long* strides_host, int dq_is_bf16, int extra_key_major, void* stream);
 
 /* fp32 -> bf16 */
 int gd_cast_f32_to_bf16(const float* src, void* dst, long n, void* stream);
@@ -145,8 +145,9 @@ int gd_removal_corr_sm100(const void* q_b, const void* k_b, const float* lse_b, 
 int gd_attn_probs_rows2(const void* q, const void* k, const float* lse, const int* j2, int M, int H, int N, int Nk, int d, float scale,
                         void* p2_out, int ldp, const long* qk_strides_host, void* stream);
 
-/* extra[h, m, :] = g2[h*M+m].x * p2[h, m, :] + g2[h*M+m].y * p2[h, M+m, :]  (H, M, ld) fp32: dL/dA_e rows for gd_attn_bwd*. */
-int gd_removal_extra_rows(const void* p2_bf16, const float* g2, int H, int M, int Nk, int ld, float* extra, void* stream);
+/* extra[h, m, :] = g2[h*M+m].x * p2[h, m, :] + g2[h*M+m].y * p2[h, M+m, :]: dL/dA_e rows for gd_attn_bwd*.  key_major = 0: (H, M, ld) fp32;
+ * key_major = 1: transposed, (H, Nk, Mp) fp32 with Mp = M rounded up to 4 -- the layout gd_attn_bwd_sm100 reads coalesced. */
+int gd_removal_extra_rows(const void* p2_bf16, const float* g2, int H, int M, int Nk, int ld, float* extra, int key_major, void* stream);
 
 /* attention_processors.py:231-246 (sim), 283-287 (movement), 289-305 (amodal, target t), loss.py:22-41 (smoothness): unweighted partial
  * sums (n_partials,5) and grad = d(weighted loss)/d replace_out.  c_* = weight / denominator of each term. */

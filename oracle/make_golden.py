@@ -203,6 +203,28 @@ def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_ste
             rec["dq_removal_absmax"] = np.float64(np.abs(rq.numpy()).max())
             rec["loss_removal_only"] = np.float64(float(c2.loss))
             print(f"  removal-only loss {float(c2.loss):.6f}, |dq| max {np.abs(rq.numpy()).max():.3e}")
+            # The removal term differentiates through max / arg-max over the masked correlation (attention_processors.py:256-266): its gradient
+            # jumps where the two largest candidates of a row tie.  Store the decision and its margin per (head, inpaint row), so that a test
+            # can hold the max-norm gate on the rows whose decision is not a near-tie and count the others.
+            with torch.no_grad():
+                cb = c.coords_base
+                A_b = O.attention(q2[cb[0] * H: cb[1] * H].detach(), k2[cb[0] * H: cb[1] * H].detach(), v2[cb[0] * H: cb[1] * H].detach(), scale)[0]
+                inp_rows = torch.from_numpy(np.asarray(inp).reshape(-1) > 0.5)
+                corr = torch.bmm(res["A_e"].detach()[:, inp_rows], A_b.transpose(1, 2))
+                if kind == "edit":
+                    mk = O.build_masks(geo["mask"], geo["mnw"][0, 0].numpy(), geo["amodal"], S)
+                    m_in_S, m_bg_S = mk["mask_1_empty"].reshape(-1), mk["mask_wo_edit"].reshape(-1)
+                else:
+                    m_in_S = np.asarray(inp, np.float32).reshape(-1)
+                    m_bg_S = O.binarize(np.ones_like(m_in_S) - m_in_S).reshape(-1)
+                for nm, msk in (("in", m_in_S), ("bg", m_bg_S)):
+                    top = torch.topk(corr * torch.from_numpy(np.ascontiguousarray(msk, dtype=np.float32)), 2, dim=-1)
+                    rec[f"rem_j_{nm}"] = top.indices[..., 0].numpy().astype(np.int32)
+                    rec[f"rem_gap_{nm}"] = ((top.values[..., 0] - top.values[..., 1]) / top.values[..., 0].clamp_min(1e-30)).numpy().astype(np.float32)
+                rec["rem_rows"] = np.nonzero(inp_rows.numpy())[0].astype(np.int32)
+                print(f"  removal decisions: {corr.shape[0] * corr.shape[1]} (head, row) pairs, share with both margins > 1e-2: "
+                      f"{float(((rec['rem_gap_in'] > 1e-2) & (rec['rem_gap_bg'] > 1e-2)).mean()):.3f}, > 1e-3: "
+                      f"{float(((rec['rem_gap_in'] > 1e-3) & (rec['rem_gap_bg'] > 1e-3)).mean()):.3f}")
         if kind == "edit":
             rec["term_amodal"] = np.float64(float(res["terms"]["amodal"]))
     rec["meta"] = np.array([S, H, d, int(is_cross), int(use_cfg), seed, cur_step])

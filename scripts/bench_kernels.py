@@ -60,7 +60,7 @@ def fwd_case(entry, G, H, N, d, check=True):
     print(f"{entry:22s} G={G} H={H} N={N:5d} d={d:3d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr O {err:.2e} LSE {errl:.2e}", flush=True)
 
 
-def bwd_case(H, N, d, M=0, sm100=False):
+def bwd_case(H, N, d, M=0, sm100=False, clustered=False):
     g = torch.Generator(device="cuda").manual_seed(N + d)
     q, k, v = mk(g, H, N, d), mk(g, H, N, d), mk(g, H, N, d)
     do = mk(g, H, N, d, s=1.0)
@@ -75,16 +75,20 @@ def bwd_case(H, N, d, M=0, sm100=False):
     ld = (N + 7) // 8 * 8
     extra = rowmap = dl = None
     if M:
-        rows = torch.randperm(N, device="cuda")[:M].sort().values.int()
+        rows = (torch.arange(M, device="cuda") + N // 3) if clustered else torch.randperm(N, device="cuda")[:M].sort().values
+        rows = rows.int()
         rowmap = torch.full((N,), -1, device="cuda", dtype=torch.int32)
         rowmap[rows.long()] = torch.arange(M, device="cuda", dtype=torch.int32)
         extra = torch.randn(H, M, ld, device="cuda") * 0.01
         dl = torch.ones(1, device="cuda")
+        Mp = (M + 3) // 4 * 4
+        extra_t = torch.zeros(H, N, Mp, device="cuda")          # key-major copy: the layout the product path hands to the tcgen05 kernel
+        extra_t[:, :, :M] = extra[:, :, :N].transpose(1, 2)
 
     def run():
         if sm100:
-            call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N,
-                 d, float(scale), None, 0, stream())
+            call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra_t if M else None), ptr(dl), ptr(rowmap), Mp if M else ld, M,
+                 ptr(dq), H, N, d, float(scale), None, 0, 1 if M else 0, stream())
         else:
             call("gd_attn_bwd", 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N,
                  d, float(scale), None, 0, stream())
@@ -100,11 +104,53 @@ def bwd_case(H, N, d, M=0, sm100=False):
         # delta gets the extra term too in the real path; keep the same delta on both sides here
     ds = p * (dp - delta[..., None])
     ref = torch.einsum("hnk,hkd->hnd", ds, k.float()) * scale
-    print(f"gd_attn_bwd{'_sm100' if sm100 else '      '}(dQ)  H={H} N={N:5d} d={d:3d} M={M:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr dQ {rel(dq, ref):.2e}",
+    print(f"gd_attn_bwd{'_sm100' if sm100 else '      '}(dQ)  H={H} N={N:5d} d={d:3d} M={M:4d}{' (clustered)' if clustered else ''}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.1f} TFLOP/s  relerr dQ {rel(dq, ref):.2e}",
           flush=True)
 
 
+def corr_case(H, N, d, M):
+    """removal-loss correlation + masked arg-max: round-1 path (materialised base map, mma.sync GEMMs) against the tcgen05 kernel"""
+    g = torch.Generator(device="cuda").manual_seed(N + d + M)
+    q_b, k_b, q_e = mk(g, H, N, d), mk(g, H, N, d), mk(g, H, N, d)
+    scale = d ** -0.5
+    lse_b = torch.logsumexp(torch.einsum("hnd,hkd->hnk", q_b.float(), k_b.float()) * scale, -1).contiguous()
+    lse_e = torch.logsumexp(torch.einsum("hnd,hkd->hnk", q_e.float(), k_b.float()) * scale, -1).contiguous()
+    rows = (torch.arange(M, device="cuda") + N // 3).int()
+    m_in = torch.zeros(N, device="cuda"); m_in[rows.long()] = 1.0
+    m_bg = ((torch.rand(N, device="cuda", generator=g) > 0.3).float() * (1 - m_in)).contiguous()
+    ld = (N + 7) // 8 * 8
+    a_e = torch.empty(H, M, ld, device="cuda", dtype=torch.bfloat16)
+    call("gd_attn_probs", ptr(q_e), ptr(k_b), ptr(lse_e), ptr(rows), M, H, N, N, d, float(scale), ptr(a_e), ld, None, stream())
+    a_b = torch.empty(H, N, ld, device="cuda", dtype=torch.bfloat16)
+    p_old = torch.empty(H, (N + 63) // 64, M, 4, device="cuda")
+    p_new = torch.empty(H, N // 32, M, 4, device="cuda")
+
+    def old():
+        call("gd_attn_probs", ptr(q_b), ptr(k_b), ptr(lse_b), None, N, H, N, N, d, float(scale), ptr(a_b), ld, None, stream())
+        call("gd_corr_max_partial", ptr(a_e), ptr(a_b), H, M, N, N, ld, ptr(m_in), ptr(m_bg), ptr(p_old), stream())
+
+    def new():
+        call("gd_removal_corr_sm100", ptr(q_b), ptr(k_b), ptr(lse_b), ptr(a_e), H, M, N, d, float(scale), ld, None, ptr(m_in), ptr(m_bg), ptr(p_new), stream())
+
+    ms_old, ms_new = timed(old, iters), timed(new, iters)
+    fl = 2.0 * H * M * N * N
+    red = lambda p: (p[..., 0].amax(1), p[..., 2].amax(1))          # max over the column tiles: (H, M) for the inpaint and the background mask
+    (oi, ob), (ni, nb) = red(p_old), red(p_new)
+    # fp32 reference of the two maxima on the same bf16 maps
+    corr = torch.einsum("hmk,hnk->hmn", a_e[:, :, :N].float(), a_b[:, :, :N].float())
+    ri, rb = (corr * m_in).amax(-1), (corr * m_bg).amax(-1)
+    print(f"removal correlation    H={H} N={N:5d} d={d:3d} M={M:4d}: materialised map + mma.sync {ms_old * 1e3:8.1f} us ({fl / ms_old / 1e9:6.1f} TFLOP/s) | "
+          f"tcgen05 {ms_new * 1e3:8.1f} us ({fl / ms_new / 1e9:6.1f} TFLOP/s)  relerr vs fp32: max_in {rel(ni, ri):.2e} max_bg {rel(nb, rb):.2e} "
+          f"(mma.sync path: {rel(oi, ri):.2e} {rel(ob, rb):.2e})", flush=True)
+
+
 cfg = lambda key, value: call("gd_attn_sm100_config", key, value)
+
+if only in (None, "corr", "sweep"):
+    corr_case(8, 4096, 40, 410)
+    corr_case(8, 4096, 40, 76)
+    corr_case(8, 4096, 40, 640)
+    corr_case(8, 1024, 80, 100)
 
 if only == "sweep":
     for np_ in (-1, 0, 2, 3):
@@ -140,6 +186,8 @@ if only in (None, "fwd"):
 if only in (None, "bwd"):
     bwd_case(8, 4096, 40, sm100=True)
     bwd_case(8, 4096, 40, M=410, sm100=True)
+    bwd_case(8, 4096, 40, M=410, sm100=True, clustered=True)
+    bwd_case(8, 4096, 40, M=76, sm100=True, clustered=True)
     bwd_case(8, 1024, 80, sm100=True)
     bwd_case(8, 1024, 80, M=100, sm100=True)
     bwd_case(2, 9216, 40, sm100=True)

@@ -14,5 +14,5 @@ call("gd_attn_fwd_sm100", _lib.ptr_array([q]), _lib.ptr_array([k]), _lib.ptr_arr
 delta = (do.float() * O[0]).sum(-1).contiguous()
 dq = torch.empty(H, N, d, device="cuda")
 for _ in range(3):
-    call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), None, None, None, (N + 7) // 8 * 8, 0, ptr(dq), H, N, d, d ** -0.5, None, 0, stream())
+    call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), None, None, None, (N + 7) // 8 * 8, 0, ptr(dq), H, N, d, d ** -0.5, None, 0, 0, stream())
 torch.cuda.synchronize()

@@ -99,19 +99,25 @@ def test_sm100_backward_dq(N, d, H, M):
     delta = (p * dp).sum(-1).contiguous()          # the row term of the softmax Jacobian (what gd_attn_bwd_prep produces on the path)
     ref = torch.einsum("hnk,hkd->hnd", p * (dp - delta[..., None]), k.float()) * scale
     out = []
-    for entry in ("gd_attn_bwd_sm100", "gd_attn_bwd"):
+    # the tcgen05 kernel with the removal rows row-major (H, M, ld) and key-major (H, N, Mp) [what the product path passes], then the mma.sync kernel
+    extra_t, Mp = None, (M + 3) // 4 * 4
+    if M:
+        extra_t = torch.zeros(H, N, Mp, device="cuda")
+        extra_t[:, :, :M] = extra[:, :, :N].transpose(1, 2)
+    for entry, key_major in (("gd_attn_bwd_sm100", 0), ("gd_attn_bwd_sm100", 1), ("gd_attn_bwd", 0)):
         dq = torch.full((H, N, d), float("nan"), device="cuda", dtype=torch.float32)
         if entry == "gd_attn_bwd":
             call(entry, 0, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, N, d,
                  float(scale), None, 0, stream())
         else:
-            call(entry, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), ld, M, ptr(dq), H, N, d, float(scale),
-                 None, 0, stream())
+            call(entry, ptr(q), ptr(k), ptr(v), ptr(do), ptr(L[0]), ptr(delta), ptr(extra_t if key_major else extra), ptr(dl), ptr(rowmap),
+                 Mp if key_major else ld, M, ptr(dq), H, N, d, float(scale), None, 0, key_major if M else 0, stream())
         torch.cuda.synchronize()
         out.append(dq)
     assert torch.isfinite(out[0]).all()
     assert relerr(out[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2       # bf16 operands / bf16 dS vs fp32 math (tolerance of the path: 2e-2)
-    assert relerr(out[0].cpu().numpy(), out[1].cpu().numpy()) <= 1e-2
+    assert torch.equal(out[0], out[1])                                   # the layout of the removal rows does not change a bit
+    assert relerr(out[0].cpu().numpy(), out[2].cpu().numpy()) <= 1e-2
 
 
 @pytest.mark.parametrize("N,Nk,d,H", [(4096, 4096, 40, 8), (1024, 1024, 80, 8), (256, 256, 160, 8), (1024, 77, 80, 8), (200, 77, 40, 4)])
@@ -152,7 +158,7 @@ def test_projection_layout_is_read_and_written_in_place(N, Nk, d, H):
         args = (_lib.base_ptr(lay.sl(q_, 1)), _lib.base_ptr(lay.sl(k_, 1)), _lib.base_ptr(lay.sl(v_, 1)), ptr(do), ptr(L[0]), ptr(delta), None,
                 None, None, (Nk + 7) // 8 * 8, 0, _lib.base_ptr(lay.sl(dq, 1)))
         if sm100:
-            call("gd_attn_bwd_sm100", *args, H, N, d, float(scale), lay.strides(), 1, stream())
+            call("gd_attn_bwd_sm100", *args, H, N, d, float(scale), lay.strides(), 1, 0, stream())
         else:
             call("gd_attn_bwd", 0, *args, H, N, Nk, d, float(scale), lay.strides(), 1, stream())
         dk = torch.zeros_like(k_)
