@@ -462,72 +462,90 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
         const float* exrow = (slot >= 0) ? (p.ex_t ? p.extra + ((long)h * N + half * NC) * p.ex_ld + slot
                                                    : p.extra + ((long)h * p.M + slot) * p.ex_ld + half * NC) : nullptr;
         const bool any_ex = __any_sync(0xffffffffu, exrow != nullptr);   // warp-uniform: does this warp own removal-loss rows at all
-        for (int j = 0; j < nT; ++j) {
-            // removal-loss rows: this step's 32 floats of dL/dP are requested BEFORE the wait for the score GEMMs, so that their L2 latency
-            // runs under it (round 1 loaded them inside the arithmetic: the few CTAs that own inpaint rows then set the kernel's makespan)
-            float4 ev[NC / 4];
-            if (any_ex && exrow) {
-                if (p.ex_t) {
-                    const float* e0 = exrow + (long)j * BNK * ex_ks;
-#pragma unroll
-                    for (int i = 0; i < NC / 4; ++i)
-                        ev[i] = make_float4(__ldg(e0 + (4 * i) * ex_ks), __ldg(e0 + (4 * i + 1) * ex_ks), __ldg(e0 + (4 * i + 2) * ex_ks), __ldg(e0 + (4 * i + 3) * ex_ks));
-                } else {
-#pragma unroll
-                    for (int i = 0; i < NC / 4; ++i) ev[i] = *reinterpret_cast<const float4*>(exrow + j * BNK + 4 * i);
-                }
-            }
-            mbar_wait(s_full, j & 1);
-            tc_fence_after();
-            uint32_t sr[NC], dp[NC];
-            if (any_ex) {
-                tmem_ld32(tmem + lane_off + COL_DP + half * NC, dp);
-                tmem_wait_ld();
-                if (exrow) {
-#pragma unroll
-                    for (int i = 0; i < NC / 4; ++i) {
-                        dp[4 * i] = __float_as_uint(fmaf(ex_scale, ev[i].x, __uint_as_float(dp[4 * i])));
-                        dp[4 * i + 1] = __float_as_uint(fmaf(ex_scale, ev[i].y, __uint_as_float(dp[4 * i + 1])));
-                        dp[4 * i + 2] = __float_as_uint(fmaf(ex_scale, ev[i].z, __uint_as_float(dp[4 * i + 2])));
-                        dp[4 * i + 3] = __float_as_uint(fmaf(ex_scale, ev[i].w, __uint_as_float(dp[4 * i + 3])));
-                    }
-                }
-                tmem_ld32(tmem + lane_off + COL_S + half * NC, sr);
-                tmem_wait_ld();
+        // one pair of scores -> one packed bf16 pair of dS = P o (dP - delta)
+        auto ds_pair = [&](uint32_t s0, uint32_t s1, uint32_t g0, uint32_t g1, int c) -> uint32_t {
+            const u64 x2 = fma2(pk2u(s0, s1), sc2, nl2);
+            u64 p2;
+            if (pair_is_poly<NP>(c)) {
+                p2 = ex2_poly2(x2);
             } else {
+                float x0, x1;
+                upk2(x2, x0, x1);
+                p2 = pk2(ex2(x0), ex2(x1));
+            }
+            float d0, d1;
+            upk2(mul2(p2, add2(pk2u(g0, g1), nd2)), d0, d1);
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
+            return *reinterpret_cast<uint32_t*>(&b2);
+        };
+        if (!any_ex) {
+            for (int j = 0; j < nT; ++j) {
+                mbar_wait(s_full, j & 1);
+                tc_fence_after();
+                uint32_t sr[NC], dp[NC];
                 tmem_ld32(tmem + lane_off + COL_S + half * NC, sr);
                 tmem_ld32(tmem + lane_off + COL_DP + half * NC, dp);
                 tmem_wait_ld();
-            }
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(s_free);
-            uint32_t pk[NC / 2];
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(s_free);
+                uint32_t pk[NC / 2];
 #pragma unroll
-            for (int c = 0; c < NC / 2; ++c) {
-                const int e = 2 * c;
-                const u64 x2 = fma2(pk2u(sr[e], sr[e + 1]), sc2, nl2);
-                u64 p2;
-                if (pair_is_poly<NP>(c)) {
-                    p2 = ex2_poly2(x2);
-                } else {
-                    float x0, x1;
-                    upk2(x2, x0, x1);
-                    p2 = pk2(ex2(x0), ex2(x1));
+                for (int c = 0; c < NC / 2; ++c) pk[c] = ds_pair(sr[2 * c], sr[2 * c + 1], dp[2 * c], dp[2 * c + 1], c);
+                if (j > 0) {
+                    mbar_wait(dq_done, (j - 1) & 1);              // dS(j-1) has been consumed by its dQ product
+                    tc_fence_after();
                 }
-                const u64 g2 = pk2u(dp[e], dp[e + 1]);
-                float d0, d1;
-                upk2(mul2(p2, add2(g2, nd2)), d0, d1);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(d0, d1);
-                pk[c] = *reinterpret_cast<uint32_t*>(&b2);
+                tmem_st16(tmem + lane_off + COL_DS + half * (NC / 2), pk);
+                tmem_wait_st();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(ds_full);
             }
-            if (j > 0) {
-                mbar_wait(dq_done, (j - 1) & 1);              // dS(j-1) has been consumed by its dQ product
+        } else {
+            // Warps that own removal-loss rows: dL/dP of the row (`extra`) joins dP.  Its 32 floats per step come from L2 (~700 clk): they are
+            // requested one step AHEAD, in two groups of 16 that are re-issued as soon as the group has been folded into dP, and the step itself
+            // is walked in two 16-column halves so that the prefetch registers fit under the two-CTAs-per-SM register budget.  (Loading them
+            // inside the arithmetic made the few CTAs that own inpaint rows set the kernel's makespan: 118 us against 75 us without rows.)
+            float ev[NC];
+            auto fetch = [&](int j, int g) {
+                if (exrow && j < nT) {
+                    const float* e0 = exrow + ((long)j * BNK + g * 16) * ex_ks;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) ev[g * 16 + i] = __ldg(e0 + i * ex_ks);
+                }
+            };
+            fetch(0, 0);
+            fetch(0, 1);
+            for (int j = 0; j < nT; ++j) {
+                mbar_wait(s_full, j & 1);
                 tc_fence_after();
+                uint32_t pk[NC / 2];
+#pragma unroll
+                for (int g = 0; g < 2; ++g) {
+                    uint32_t sr[16], dp[16];
+                    tmem_ld16(tmem + lane_off + COL_S + half * NC + g * 16, sr);
+                    tmem_ld16(tmem + lane_off + COL_DP + half * NC + g * 16, dp);
+                    tmem_wait_ld();
+                    if (g == 1) {
+                        tc_fence_before();
+                        if (lane == 0) mbar_arrive(s_free);
+                    }
+                    if (exrow) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) dp[i] = __float_as_uint(fmaf(ex_scale, ev[g * 16 + i], __uint_as_float(dp[i])));
+                    }
+                    fetch(j + 1, g);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) pk[g * 8 + c] = ds_pair(sr[2 * c], sr[2 * c + 1], dp[2 * c], dp[2 * c + 1], g * 8 + c);
+                }
+                if (j > 0) {
+                    mbar_wait(dq_done, (j - 1) & 1);
+                    tc_fence_after();
+                }
+                tmem_st16(tmem + lane_off + COL_DS + half * (NC / 2), pk);
+                tmem_wait_st();
+                tc_fence_before();
+                if (lane == 0) mbar_arrive(ds_full);
             }
-            tmem_st16(tmem + lane_off + COL_DS + half * (NC / 2), pk);
-            tmem_wait_st();
-            tc_fence_before();
-            if (lane == 0) mbar_arrive(ds_full);
         }
         // epilogue: dQ * scale -> global; the two warps of a quarter split the 16-column chunks
         mbar_wait(dq_done, (nT - 1) & 1);

@@ -12,11 +12,14 @@ The kernels of the path launch on torch's current stream (`_lib.stream()`), whic
 """
 import contextlib
 import gc
+import threading
 
 import torch
 
 from . import _lib
 
+_CAPTURE_LOCK = threading.RLock()   # one capture at a time per process: the garbage collector is paused around it (runner.EditWorkers runs
+                                    # several edits of one GPU from several threads)
 ENABLED = True      # product default; tests compare against the eager path by switching it off
 GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as well
 
@@ -27,23 +30,25 @@ def _capture(graph, pool, stream, sync=True):
     captures one graph per request, and an emptied allocator cache makes every eager allocation after it pay for cudaMalloc again, so the capture
     is driven by hand.  The cyclic garbage collector is paused: a collection in the middle of a capture may destroy an older CUDAGraph or free
     its tensors, which invalidates the capture in progress."""
-    was = gc.isenabled()
-    gc.disable()
-    cur = torch.cuda.current_stream(stream.device)
-    if sync:
-        torch.cuda.synchronize(stream.device)
-    stream.wait_stream(cur)
-    try:
-        with torch.cuda.stream(stream):
-            graph.capture_begin(pool=pool)
-            try:
-                yield
-            finally:
-                graph.capture_end()
-    finally:
-        cur.wait_stream(stream)
-        if was:
-            gc.enable()
+    with _CAPTURE_LOCK:
+        was = gc.isenabled()
+        gc.disable()
+        cur = torch.cuda.current_stream(stream.device)
+        if sync:
+            cur.synchronize()       # (the current stream only: another edit lane of this GPU may be busy on its own streams)
+        stream.wait_stream(cur)
+        try:
+            with torch.cuda.stream(stream):
+                # thread_local: CUDA calls that other threads make meanwhile (another lane's allocations, event queries) stay legal
+                graph.capture_begin(pool=pool, capture_error_mode="thread_local")
+                try:
+                    yield
+                finally:
+                    graph.capture_end()
+        finally:
+            cur.wait_stream(stream)
+            if was:
+                gc.enable()
 
 
 def _pool(model):

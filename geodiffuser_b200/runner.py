@@ -42,6 +42,53 @@ def run_requests(model, requests, rank=0, world_size=1, edit_fn=None):
     return out, time.perf_counter() - t0
 
 
+class EditWorkers:
+    """`lanes` independent edits in flight on ONE GPU: one host thread, CUDA stream and model replica (shared weights, own processors /
+    controller / graphs / caches: unet_sd15.replicate_model) per lane, requests dealt round-robin to the lanes.  Still request-level
+    parallelism with no exchange between edits: every edit runs exactly the kernels, in the order, it runs alone, so its result does not
+    depend on the lane count.  Why: one edit is a chain of ~90 000 dependent launches of mostly small kernels (8^2 .. 64^2 tokens, batch 2-3)
+    that individually cannot fill 148 SMs; a second independent chain fills the gaps."""
+
+    def __init__(self, model, lanes=2):
+        from .unet_sd15 import replicate_model
+
+        self.device = model.device
+        self.models = [model] + [replicate_model(model) for _ in range(max(1, lanes) - 1)]
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in self.models]
+
+    def map(self, fn, items):
+        """results[i] = fn(lane's model, items[i]); returns after every lane's work has been queued and the calling stream waits for it"""
+        import threading
+
+        n = len(self.models)
+        results, errors = [None] * len(items), []
+        cur = torch.cuda.current_stream(self.device)
+
+        def work(w):
+            try:
+                torch.cuda.set_device(self.device)
+                self.streams[w].wait_stream(cur)
+                with torch.cuda.stream(self.streams[w]):
+                    for i in range(w, len(items), n):
+                        results[i] = fn(self.models[w], items[i])
+            except BaseException as e:   # noqa: BLE001 -- re-raised in the caller's thread
+                errors.append(e)
+
+        if n == 1 or len(items) <= 1:
+            work(0)
+        else:
+            threads = [threading.Thread(target=work, args=(w,)) for w in range(n)]
+            for t in threads:
+                t.start()
+            for t in threads:
+                t.join()
+        for s in self.streams:
+            cur.wait_stream(s)
+        if errors:
+            raise errors[0]
+        return results
+
+
 # ---- experiment-folder format of the reference's batch driver (SURVEY 8(f) N2) ---------------------------------------------------------
 # ui_utils.save_exp / read_exp (:52-159) and large_scale_editor.py:133-178, 349-399: one edit = one folder holding input_image.png,
 # input_mask.png, depth.npy, transform.npy, image_shape.npy; results are written next to them (loss.pkl; the reference also decodes

@@ -343,6 +343,28 @@ class EditModel:
         return self._unets[dt]
 
 
+def replicate_model(model):
+    """A second EditModel over the SAME weight tensors: own module objects, attention processors, scheduler state, CUDA graphs and cache
+    arenas (everything an edit mutates), shared parameters and buffers (nothing an edit mutates).  runner.EditWorkers uses one replica per
+    concurrent edit lane of a GPU."""
+    import copy
+    from .attention_processors import VanillaAttentionProcessor
+    from .diffusion import DDIMScheduler
+
+    model.unet      # materialise the body in the current caller precision before copying the module tree
+    new = EditModel.__new__(EditModel)
+    new.scheduler, new.device, new._unets = DDIMScheduler(), model.device, {}
+    for dt, u in model._unets.items():
+        procs = u.attn_processors
+        u.set_attn_processor(None)
+        memo = {id(t): t for t in list(u.parameters()) + list(u.buffers())}      # deepcopy maps every weight tensor to itself: shared
+        c = copy.deepcopy(u, memo)
+        u.set_attn_processor(procs)
+        c.set_attn_processor(VanillaAttentionProcessor())
+        new._unets[dt] = c
+    return new
+
+
 def build_model(device="cuda", seed=1234, tiny=False):
     """Random-init SD-1.5 topology under torch.manual_seed(seed) (CPU generator => identical weights on every box)."""
     from .diffusion import DDIMScheduler

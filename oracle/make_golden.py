@@ -290,11 +290,18 @@ def product_shape_cases(R, geos=None):
     attention_case(R, "remove_self_S64_H8d40_opt", geos["remove"], "remove", 64, 8, 40, False, False, 203, subsample=16)
     attention_case(R, "edit_self_S32_H8d80_opt", geos["translate2d"], "edit", 32, 8, 80, False, False, 204, subsample=8)
     attention_case(R, "remove_self_S32_H8d80_opt", geos["remove"], "remove", 32, 8, 80, False, False, 205, subsample=8)
+    config3_case(R)
 
 
-def geometry_only(R, cfg):
+def config3_case(R):
+    """BASELINE.json configs[3]: a 768 x 768 image -> 96^2 latent, N = 9216 tokens in the first self-attention level, where the amodal term
+    is active as well (N > 32^2, attention_processors.py:596-597).  H = 2 heads keep the reference's materialised (H, N, N) maps in memory."""
+    attention_case(R, "edit_self_S96_H2d40_opt_768", geometry_only(R, "rotate3d", size=768), "edit", 96, 2, 40, False, False, 206, subsample=32)
+
+
+def geometry_only(R, cfg, size=512):
     """what geometry_case returns, without re-writing its golden file"""
-    image, depth, mask, T = synth.edit_inputs(cfg)
+    image, depth, mask, T = synth.edit_inputs(cfg, size=size)
     (pimg, valid, dproj, coords_ref, pmask_ref), d_used, mask_t = R.get_transform_coordinates_cpu(
         image / 255.0, depth.copy(), mask.copy(), T, return_mesh=True)
     coords_ref = coords_ref[0].numpy()
@@ -308,6 +315,9 @@ def geometry_only(R, cfg):
 
 
 if __name__ == "__main__":
+    if "--config3" in sys.argv:
+        torch.set_grad_enabled(True)
+        sys.exit(config3_case(load_reference()))
     if "--product-shapes" in sys.argv:     # only the H = 8 cases (the rest of the golden set is left untouched)
         torch.set_grad_enabled(True)
         sys.exit(product_shape_cases(load_reference()))

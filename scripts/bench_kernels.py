@@ -146,7 +146,7 @@ def corr_case(H, N, d, M):
 
 cfg = lambda key, value: call("gd_attn_sm100_config", key, value)
 
-if only in (None, "corr", "sweep"):
+if only in ("corr", "sweep"):
     corr_case(8, 4096, 40, 410)
     corr_case(8, 4096, 40, 76)
     corr_case(8, 4096, 40, 640)
