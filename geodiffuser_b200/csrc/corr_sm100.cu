@@ -10,13 +10,13 @@
 // 64-wide steps:
 //
 //     S    = Q_b[n tile] K_b[k tile]^T                      tcgen05.mma SS (Q, K from shared memory via TMA), fp32 in TMEM
-//     P_b  = exp2(S * scale * log2e - lse_b[n] * log2e)     four softmax warps, thread = base row n = TMEM lane; bf16 back into TMEM
+//     P_b  = exp2(S * scale * log2e - lse_b[n] * log2e)     eight softmax warps, two threads per base row n = TMEM lane (32 keys each); bf16 back into TMEM
 //     D   += P_b A_e[m chunk, k tile]^T                     tcgen05.mma TS: A = P_b from TMEM, B = the A_e rows (K-major, via TMA)
 //
 // i.e. the base-map tile is recomputed on the fly from q_b, k_b and the stored log-sum-exp, lives only in TMEM, and the accumulator
 // D (128 n x MC m, fp32, <= 256 TMEM columns) holds corr^T for the whole key range.  Epilogue: D is read back 32 columns at a time,
 // transposed through a warp-private shared-memory tile, and every thread scans one column m over the warp's 32 base rows for the two
-// masked (max, first argmax) pairs: partial[h, 4 * n_tile + warp, m] -- the layout gd_removal_finalize already reduces.
+// masked (max, first argmax) pairs: partial[h, 4 * n_tile + lane quarter, m] -- the layout gd_removal_finalize already reduces.
 // A_e[rows] itself (H x M x N bf16, ~27 MB at the 64^2 level) is produced by gd_attn_probs as before.
 //
 // TMEM: S [0,64) | P double buffer [64,96) [96,128) | D [128, 128 + MC).  Roofline: tensor pipe (dense BF16); per key step the
@@ -25,7 +25,7 @@
 
 namespace gd {
 
-constexpr int CORR_THREADS = 192;
+constexpr int CORR_THREADS = 320;     // warps 0-7 softmax (lane quarter x key half), 8 = TMA, 9 = MMA issuer
 constexpr int CORR_BM = 128;      // base rows per CTA
 constexpr int CORR_BK = 64;       // keys per step
 
@@ -57,8 +57,8 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
     const int STAGE_BYTES = (K_BYTES + A_BYTES + 1023) & ~1023;
     unsigned char* sQ = smem;
     unsigned char* sStage = sQ + Q_BYTES;                  // n_stage x { K tile, A_e tile }
-    unsigned char* sT = sStage + p.n_stage * STAGE_BYTES;  // epilogue transpose tiles: 4 warps x [32][33] floats
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sT + 4 * 32 * 33 * 4);
+    unsigned char* sT = sStage + p.n_stage * STAGE_BYTES;  // epilogue transpose tiles: 8 warps x [32][33] floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sT + 8 * 32 * 33 * 4);
     uint64_t* q_full = bars + 0;
     uint64_t* s_full = bars + 1;
     uint64_t* s_free = bars + 2;
@@ -76,22 +76,22 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
     const int NS = p.n_stage;
 
     if (threadIdx.x == 0) {
-        mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(d_done, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(p_full + s, 4); mbar_init(p_free + s, 1); }
+        mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(s_free, 8); mbar_init(d_done, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(p_full + s, 8); mbar_init(p_free + s, 1); }
         for (int s = 0; s < MAX_STAGE; ++s) { mbar_init(st_full + s, 1); mbar_init(st_empty + s, 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 5) {
+    if (warp == 9) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp == 4 && lane == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.a); }
+    if (warp == 8 && lane == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.a); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ================= TMA producer =================
         if (lane == 0) {
             mbar_expect_tx(q_full, Q_BYTES);
@@ -108,7 +108,7 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
                 tma_load_3d(dst + K_BYTES, &maps.a, st_full + s, j * CORR_BK, m0, h);     // rows past M are zero-filled
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ================= MMA issuer =================
         if (lane == 0) {
             constexpr uint32_t IDESC_S = make_idesc(CORR_BM, CORR_BK, 0, 0);
@@ -143,54 +143,52 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
             tc_commit(d_done);
         }
     } else {
-        // ================= softmax warps 0-3: thread = base row n = TMEM lane =================
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
-        const int n = n0 + warp * 32 + lane;
+        // ================= softmax warps 0-7: (lane quarter, key half); two threads share a base row n = TMEM lane =================
+        const int quarter = warp & 3, half = warp >> 2;
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const int n = n0 + quarter * 32 + lane;
         const float lse2 = p.lse[(long)h * N + n] * 1.4426950408889634f;
         const u64 sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-lse2, -lse2);
         for (int j = 0; j < nT; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            uint32_t sr[CORR_BK];
-            tmem_ld32(tmem + lane_off + COL_S, sr);
-            tmem_ld32(tmem + lane_off + COL_S + 32, sr + 32);
+            uint32_t sr[32];
+            tmem_ld32(tmem + lane_off + COL_S + half * 32, sr);
             tmem_wait_ld();
             tc_fence_before();
             if (lane == 0) mbar_arrive(s_free);
             const int b = j & 1;
+            uint32_t pk[16];
 #pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-                uint32_t pk[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    float x0, x1;
-                    upk2(fma2(pk2u(sr[cc * 32 + 2 * c], sr[cc * 32 + 2 * c + 1]), sc2, nl2), x0, x1);
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2(x0), ex2(x1));
-                    pk[c] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-                if (cc == 0 && j >= 2) {
-                    mbar_wait(p_free + b, ((j - 2) >> 1) & 1);     // D(j-2) has consumed this P buffer
-                    tc_fence_after();
-                }
-                tmem_st16(tmem + lane_off + COL_P + b * 32 + cc * 16, pk);
+            for (int c = 0; c < 16; ++c) {
+                float x0, x1;
+                upk2(fma2(pk2u(sr[2 * c], sr[2 * c + 1]), sc2, nl2), x0, x1);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(ex2(x0), ex2(x1));
+                pk[c] = *reinterpret_cast<uint32_t*>(&b2);
             }
+            if (j >= 2) {
+                mbar_wait(p_free + b, ((j - 2) >> 1) & 1);     // D(j-2) has consumed this P buffer
+                tc_fence_after();
+            }
+            tmem_st16(tmem + lane_off + COL_P + b * 32 + half * 16, pk);
             tmem_wait_st();
             tc_fence_before();
             if (lane == 0) mbar_arrive(p_full + b);
         }
-        // ---- epilogue: masked (max, first argmax) over this warp's 32 base rows for every inpaint row m of the chunk ----
+        // ---- epilogue: masked (max, first argmax) over this lane quarter's 32 base rows for every inpaint row m of the chunk;
+        //      the two warps of a quarter take alternate 32-column blocks of D ----
         mbar_wait(d_done, 0);
         tc_fence_after();
         float* tile = reinterpret_cast<float*>(sT) + warp * 32 * 33;
         const float mi = p.mask_in[n], mb = p.mask_bg[n];
         const int n_part = 4 * (N / CORR_BM);
-        float4* out = p.partial + ((long)h * n_part + (4 * blockIdx.x + warp)) * p.M;
-        const int nbase = n0 + warp * 32;
-        for (int c0 = 0; c0 < MC; c0 += 32) {
+        float4* out = p.partial + ((long)h * n_part + (4 * blockIdx.x + quarter)) * p.M;
+        const int nbase = n0 + quarter * 32;
+        for (int c0 = half * 32; c0 < MC; c0 += 64) {
             uint32_t v[32];
             if (MC - c0 >= 32) {
                 tmem_ld32(tmem + lane_off + COL_D + c0, v);
-            } else {                                            // MC is a multiple of 16: last half chunk
+            } else {                                            // MC is a multiple of 16: last half block
                 tmem_ld16(tmem + lane_off + COL_D + c0, v);
 #pragma unroll
                 for (int i = 16; i < 32; ++i) v[i] = 0u;
@@ -219,7 +217,7 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (warp == 9) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
     }
@@ -228,7 +226,7 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
 template <int D> static int launch_corr(const CorrMaps& maps, const CorrParams& p, int n_chunks, cudaStream_t st) {
     constexpr int KB = (D + 63) / 64;
     const int stage = (KB * CORR_BK * 128 + p.MC * 128 + 1023) & ~1023;
-    const size_t smem = (size_t)KB * 128 * 128 + (size_t)p.n_stage * stage + 4 * 32 * 33 * 4 + 256 + 1024;
+    const size_t smem = (size_t)KB * 128 * 128 + (size_t)p.n_stage * stage + 8 * 32 * 33 * 4 + 256 + 1024;
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(removal_corr_sm100_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -271,7 +269,7 @@ extern "C" int gd_removal_corr_sm100(const void* q_b, const void* k_b, const flo
     p.H = H; p.N = N; p.M = M; p.MC = MC; p.scale2 = scale * 1.4426950408889634f;
     const int kb = (d + 63) / 64;
     const int stage = (kb * CORR_BK * 128 + MC * 128 + 1023) & ~1023;
-    p.n_stage = (int)((200 * 1024 - kb * 128 * 128) / stage);
+    p.n_stage = (int)((184 * 1024 - kb * 128 * 128) / stage);
     if (p.n_stage > 4) p.n_stage = 4;
     if (p.n_stage < 2) return set_error(GD_ERR_UNSUPPORTED, "gd_removal_corr_sm100: stage of %d bytes does not fit twice", stage);
     if (d == 40) return launch_corr<40>(maps, p, n_chunks, (cudaStream_t)stream);

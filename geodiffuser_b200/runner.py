@@ -43,50 +43,62 @@ def run_requests(model, requests, rank=0, world_size=1, edit_fn=None):
 
 
 class EditWorkers:
-    """`lanes` independent edits in flight on ONE GPU: one host thread, CUDA stream and model replica (shared weights, own processors /
-    controller / graphs / caches: unet_sd15.replicate_model) per lane, requests dealt round-robin to the lanes.  Still request-level
-    parallelism with no exchange between edits: every edit runs exactly the kernels, in the order, it runs alone, so its result does not
-    depend on the lane count.  Why: one edit is a chain of ~90 000 dependent launches of mostly small kernels (8^2 .. 64^2 tokens, batch 2-3)
-    that individually cannot fill 148 SMs; a second independent chain fills the gaps."""
+    """`lanes` independent edits in flight on ONE GPU: one persistent host thread, CUDA stream and model replica (shared weights, own
+    processors / controller / graphs / caches: unet_sd15.replicate_model) per lane, requests dealt round-robin to the lanes.  Still
+    request-level parallelism with no exchange between edits: every edit runs exactly the kernels, in the order, it runs alone, so its result
+    does not depend on the lane count.  Why: one edit is a chain of ~90 000 dependent launches of mostly small kernels (8^2 .. 64^2 tokens,
+    batch 2-3) that individually cannot fill 148 SMs; a second independent chain fills the gaps.
+    The threads are persistent because cuDNN's autotune cache (torch.backends.cudnn.benchmark) is per host thread: a fresh thread would
+    re-tune the body's convolutions, which is illegal inside the stream capture of an edit's optimisation pass."""
 
     def __init__(self, model, lanes=2):
+        import queue
+        import threading
         from .unet_sd15 import replicate_model
 
-        self.device = model.device
+        dev = model.device
+        self.device = dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
         self.models = [model] + [replicate_model(model) for _ in range(max(1, lanes) - 1)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.models]
+        self._jobs = [queue.Queue() for _ in self.models]
+        self._done = queue.Queue()
+        self._threads = [threading.Thread(target=self._lane, args=(w,), daemon=True) for w in range(len(self.models))]
+        for t in self._threads:
+            t.start()
+
+    def _lane(self, w):
+        torch.cuda.set_device(self.device)
+        while True:
+            job = self._jobs[w].get()
+            if job is None:
+                return
+            fn, item, idx, after = job
+            try:
+                self.streams[w].wait_stream(after)
+                with torch.cuda.stream(self.streams[w]):
+                    self._done.put((idx, fn(self.models[w], item), None))
+            except BaseException as e:   # noqa: BLE001 -- re-raised in the caller's thread
+                self._done.put((idx, None, e))
 
     def map(self, fn, items):
-        """results[i] = fn(lane's model, items[i]); returns after every lane's work has been queued and the calling stream waits for it"""
-        import threading
-
+        """results[i] = fn(lane's model, items[i]); returns once every lane has queued its work, with the calling stream waiting for all lanes"""
         n = len(self.models)
-        results, errors = [None] * len(items), []
         cur = torch.cuda.current_stream(self.device)
-
-        def work(w):
-            try:
-                torch.cuda.set_device(self.device)
-                self.streams[w].wait_stream(cur)
-                with torch.cuda.stream(self.streams[w]):
-                    for i in range(w, len(items), n):
-                        results[i] = fn(self.models[w], items[i])
-            except BaseException as e:   # noqa: BLE001 -- re-raised in the caller's thread
-                errors.append(e)
-
-        if n == 1 or len(items) <= 1:
-            work(0)
-        else:
-            threads = [threading.Thread(target=work, args=(w,)) for w in range(n)]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
+        for i, item in enumerate(items):
+            self._jobs[i % n].put((fn, item, i, cur))
+        results, error = [None] * len(items), None
+        for _ in items:
+            idx, res, err = self._done.get()
+            results[idx], error = res, (err if err is not None and error is None else error)
         for s in self.streams:
             cur.wait_stream(s)
-        if errors:
-            raise errors[0]
+        if error is not None:
+            raise error
         return results
+
+    def close(self):
+        for q in self._jobs:
+            q.put(None)
 
 
 # ---- experiment-folder format of the reference's batch driver (SURVEY 8(f) N2) ---------------------------------------------------------
