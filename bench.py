@@ -265,6 +265,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), res
 
+    if args.workload == "mixed64":
+        return run_mixed64(args, world, rank, dev, workers, barrier)
     res = workers.map(lambda m, _: api(m), list(range(max(args.warmup, 3) * args.lanes)))     # every lane warms up (graphs, cuDNN autotune)
     out, h2d, d2h = res[-1]
     assert torch.isfinite(out).all()
@@ -322,6 +324,47 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_mixed64(args, world, rank, dev, workers, barrier):
+    """BASELINE.json configs[4]: 64 independent mixed edits -- 16 each of 2-D translation, 3-D rotation, object removal and 3-D rotation at
+    768 x 768 -- in the seed-1234 shuffle of SURVEY 8(d), dealt round-robin to the ranks (runner.shard_round_robin) and, inside a rank, to its
+    edit lanes.  Every request goes through the public API with host buffers (H2D + D2H inside the timed region).  One JSON line (rank 0)."""
+    import torch.distributed as dist
+    from geodiffuser_b200 import editor, runner
+
+    kinds = ["translate2d", "rotate3d", "remove", "rotate3d@768"] * 16
+    np.random.RandomState(1234).shuffle(kinds)
+    make = lambda i, k: editor.synthetic_request(k.split("@")[0], seed=1234 + i, image_size=768 if k.endswith("@768") else 512)
+    mine = runner.shard_round_robin(len(kinds), rank, world)
+    reqs = [make(i, kinds[i]) for i in mine]
+    api = lambda m, r: editor.perform_geometric_edit(m, r["depth"], r["image_mask"], r["transform_in"], r["text_embeddings"], r["uncond_embeddings"],
+                                                     r["x0"], r["edit_type"])
+    # warm-up: every lane sees every kind twice (inversion / CFG graphs, cuDNN autotune per lane thread, first-edit eager optimisation pass)
+    warm = [make(1000 + j, k) for k in ("translate2d", "rotate3d", "remove", "rotate3d@768") for j in range(2 * args.lanes)]
+    workers.map(api, warm)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = workers.map(api, reqs)
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    assert all(torch.isfinite(r[0]).all() for r in res)
+    if rank == 0:
+        t = float(ms) / 1e3
+        line = {"metric": METRIC, "value": len(kinds) / t, "unit": "edits/s", "n_gpus": world, "steps": len(kinds), "warmup": len(warm), "ms_per_step": t * 1e3 / len(kinds),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "configs[4]: 64 independent mixed edits (16 x 2-D translation, 16 x 3-D rotation, 16 x removal, 16 x 3-D rotation at 768^2), "
+                                       "seed-1234 shuffle, sharded round-robin over the GPUs", "parallelism": f"request-level dp{world}, {args.lanes} edit lanes per GPU",
+                           "edits_per_rank": len(mine)},
+                "e2e": {"value": len(kinds) / t, "unit": "edits/s", "h2d_bytes_per_step": int(np.mean([r[1] for r in res])), "d2h_bytes_per_step": int(np.mean([r[2] for r in res]))},
+                "lanes_per_gpu": args.lanes, "seconds": t}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -329,6 +372,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config1", choices=["config1", "mixed64"],
+                    help="config1 = BASELINE configs[1] (the metric's configuration); mixed64 = configs[4], the 64-edit mixed sweep")
     ap.add_argument("--lanes", type=int, default=2, help="independent edits in flight per GPU (1 = one edit at a time)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -82,6 +82,7 @@ class GraphedUNet:
         self.path_flops = 0.0           # their algorithmic attention-path FLOP (_lib.FLOPS)
         self.after_eval = after_eval
         self.warmup_left = warmup
+        self.warm_threads = set()       # host threads that have evaluated this pass eagerly (cuDNN autotune cache / cuBLAS handle are per thread)
         self.pool = pool
         self.stream = stream if stream is not None else torch.cuda.Stream(device=dev)
 
@@ -96,8 +97,10 @@ class GraphedUNet:
         self.context.copy_(context)
         self.t.fill_(int(t))
         if self.graph is None:
-            if self.warmup_left > 0:
-                self.warmup_left -= 1
+            tid = threading.get_ident()
+            if self.warmup_left > 0 or tid not in self.warm_threads:
+                self.warmup_left = max(0, self.warmup_left - 1)
+                self.warm_threads.add(tid)
                 return self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
             g = torch.cuda.CUDAGraph()
             l0, f0 = _lib.LAUNCHES, _lib.FLOPS
@@ -252,8 +255,9 @@ def grad_pass(model, controller, latents, context, t):
     # (cuDNN's benchmark cache is keyed on these global switches as well: a capture after one of them changed would have to autotune inside
     # the capture, which cuDNN cannot do)
     cd = torch.backends.cudnn
+    # (... and both cuDNN's autotune cache and the cuBLAS handle are per host thread: runner.EditWorkers drives a model from its lane's thread)
     wkey = (type(controller).__name__, tuple(latents.shape), tuple(context.shape), id(model.unet), cd.benchmark, cd.allow_tf32, cd.deterministic,
-            torch.backends.cuda.matmul.allow_tf32)
+            torch.backends.cuda.matmul.allow_tf32, threading.get_ident())
     if g is None and wkey in warmed and _prebuild_caches(model, controller, latents):
         # recorded without a device synchronisation: when the caches were built before the inversion (editor.run_edit) nothing here waits for
         # the GPU, so the ~45 ms of host work of the capture hide under the inversion replays still in flight
