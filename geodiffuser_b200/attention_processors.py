@@ -178,8 +178,9 @@ class AttentionControl(abc.ABC):
 
 
 class AttentionStore(AttentionControl):
-    """attention_sharing.py:158-207.  Attention maps are never materialised by the fused kernel; `store_attention_maps` (maps of
-    N <= 16^2 only in the reference, :175) is therefore served by an explicit probability kernel when requested."""
+    """attention_sharing.py:158-207.  Attention maps are never materialised by the fused kernel; what the reference stores (maps of
+    N <= 16^2 query tokens, :166-179; the geometry controllers' `store_attention_maps`, attention_processors.py:452-454, 562-564) is served by an
+    explicit probability kernel (functional.attention_maps) when requested."""
 
     @staticmethod
     def get_empty_store():
@@ -187,6 +188,8 @@ class AttentionStore(AttentionControl):
 
     def forward(self, q, k, v, is_cross: bool, place_in_unet: str, transform_coords=None, scale=None, mask=None):
         heads = q.shape[0] // max(1, getattr(self, "batch_size", 1))
+        if q.shape[1] <= 16 ** 2:      # :166-169: the maps of the small levels are kept
+            self.attn_store(Fn.attention_maps(q, k, scale, heads), is_cross, place_in_unet)
         return Fn.plain_attention(q, k, v, scale, heads)
 
     def attn_store(self, attn, is_cross: bool, place_in_unet: str):
@@ -362,6 +365,16 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         if with_loss:
             self.loss = self.loss + loss
             self.loss_log_dict["num_layers"] += 1
+        if self.use_cfg and self.store_attention_maps and N <= 16 ** 2:
+            # attention_processors.py:452-454, 562-564: the edit stream's map (edit queries against the base keys; its own text keys on cross
+            # layers).  A pass that stores maps runs eagerly (graphs.edit_pass): the store is host state.
+            ce, cb = int(self.coords_edit[0]), int(self.coords_base[0])
+            lay = Fn._Layout(q.t if isinstance(q, Fn.ProjView) else q, k.t if isinstance(k, Fn.ProjView) else k, h, isinstance(q, Fn.ProjView))
+            qt, kt = (q.t if isinstance(q, Fn.ProjView) else q), (k.t if isinstance(k, Fn.ProjView) else k)
+            q_e, k_e = lay.sl(qt, ce), lay.sl(kt, ce if is_cross else cb)
+            if isinstance(q, Fn.ProjView):
+                q_e, k_e = Fn.ProjView(q_e[None], h), Fn.ProjView(k_e[None], h)
+            self.attn_store(Fn.attention_maps(q_e, k_e, scale, h), is_cross, place_in_unet)
         return out
 
     # reference-named entry points kept for callers that invoke them directly (attention_processors.py:384, 513)

@@ -425,6 +425,30 @@ def shared_attention_layer(q, k, v, spec):
     return out, (terms[5] if terms is not None else None), terms
 
 
+def attention_maps(q, k, scale, heads, entries=None):
+    """softmax(scale q k^T) for (B*H, N, d) tensors or ProjViews, MATERIALISED: (len(entries)*H, N, Nk) fp32.  Only what the reference's
+    AttentionStore keeps (maps of N <= 16^2 query tokens, attention_sharing.py:166-179) is ever asked for: the path itself never forms a map.
+    Row sums come from a forward launch (LSE), the probabilities from gd_attn_probs."""
+    proj = isinstance(q, ProjView)
+    if proj:
+        q, k = q.t, k.t
+    lay = _Layout(q, k, heads, proj)
+    B = q.shape[0] if proj else q.shape[0] // heads
+    entries = list(range(B)) if entries is None else list(entries)
+    qb, kb = _bf16(q), _bf16(k)
+    N, Nk, d = lay.N, lay.Nk, lay.d
+    ld = (Nk + 7) // 8 * 8
+    qk_st = _lib.host_longs([lay.q[0], lay.q[1], lay.kv[0], lay.kv[1]])
+    out = torch.empty(len(entries) * heads, N, Nk, device=q.device, dtype=torch.float32)
+    for n, i in enumerate(entries):
+        qi, ki = lay.sl(qb, i), lay.sl(kb, i)
+        _, LSE = attention_forward([qi], [ki], [ki], scale, dims=(heads, N, Nk, d), strides=lay.strides())   # (values are irrelevant for the LSE)
+        p = torch.empty(heads, N, ld, device=q.device, dtype=torch.bfloat16)
+        call("gd_attn_probs", _lib.base_ptr(qi), _lib.base_ptr(ki), ptr(LSE[0]), None, N, heads, N, Nk, d, float(scale), ptr(p), ld, qk_st, stream())
+        out[n * heads:(n + 1) * heads] = p[:, :, :Nk].float()
+    return out
+
+
 def plain_attention(q, k, v, scale, heads):
     """softmax(scale q k^T) v for (B*H, N, d) tensors or ProjViews: VanillaAttentionProcessor / outside the replace window
     (attention_processors.py:120-121, 646-647).  Forward only.  The kernel writes the result in q's dtype and layout."""

@@ -22,6 +22,8 @@ _CAPTURE_LOCK = threading.RLock()   # one capture at a time per process: the gar
                                     # several edits of one GPU from several threads)
 ENABLED = True      # product default; tests compare against the eager path by switching it off
 GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as well
+CAPTURE_ERROR_MODE = "thread_local"   # cudaStreamCaptureMode of the hand-driven captures: CUDA calls that OTHER threads make meanwhile (another
+                                      # edit lane's allocations, event queries) stay legal
 
 
 @contextlib.contextmanager
@@ -39,8 +41,7 @@ def _capture(graph, pool, stream, sync=True):
         stream.wait_stream(cur)
         try:
             with torch.cuda.stream(stream):
-                # thread_local: CUDA calls that other threads make meanwhile (another lane's allocations, event queries) stay legal
-                graph.capture_begin(pool=pool, capture_error_mode="thread_local")
+                graph.capture_begin(pool=pool, capture_error_mode=CAPTURE_ERROR_MODE)
                 try:
                     yield
                 finally:
@@ -127,7 +128,7 @@ def edit_pass(model, controller, latents_input, t, context):
     the second, replayed afterwards; the controller's step counter advances exactly as in the eager evaluation."""
     # a graph captured for an earlier edit may only be replayed once THIS controller has refreshed the shared cache buffers, i.e. after its
     # first real evaluation (normally the first optimisation pass)
-    if not ENABLED or torch.is_grad_enabled() or getattr(controller, "eager_passes", 0) == 0:
+    if not ENABLED or torch.is_grad_enabled() or getattr(controller, "eager_passes", 0) == 0 or getattr(controller, "store_attention_maps", False):
         return model.unet(latents_input, t, encoder_hidden_states=context)["sample"]
     store = controller.__dict__.setdefault("_unet_graphs", {})
     arena = controller.__dict__.get("_arena")

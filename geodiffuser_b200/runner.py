@@ -78,6 +78,12 @@ class EditWorkers:
                 with torch.cuda.stream(self.streams[w]):
                     self._done.put((idx, fn(self.models[w], item), None))
             except BaseException as e:   # noqa: BLE001 -- re-raised in the caller's thread
+                import os
+                import traceback
+
+                if os.environ.get("GD_DEBUG_LANES"):
+                    print(f"[lane {w}] failed:", flush=True)
+                    traceback.print_exc()
                 self._done.put((idx, None, e))
 
     def map(self, fn, items):

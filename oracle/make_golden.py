@@ -191,7 +191,7 @@ def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_ste
                     rec["dk_loss"] = lk.numpy()
         for key, val in c.loss_log_dict["cross" if is_cross else "self"].items():
             rec["term_" + key] = np.float64(float(val))
-            check("term " + key, float(res["terms"][key]), float(val), 5e-5)
+            check("term " + key, float(res["terms"][key]), float(val), 5e-4 if subsample else 5e-5)     # (fp32 sums over N = 9216 rows differ by ~7e-5 between two summation orders)
         if subsample:
             # the SMOOTH part of the loss alone: only the removal term weighted (the L1 / TV terms have sign gradients, which no finite-precision
             # evaluation reproduces element for element: tests judge them by the share of agreeing elements, and this part by the max norm)

@@ -28,15 +28,15 @@ CASES = [  # name, geometry, kind, S, H, d, is_cross, use_cfg, seed, cur_step   
 _GEO = {}
 
 
-def geometry_for(kind):
+def geometry_for(kind, size=512):
     from geodiffuser_b200 import geometry as G
 
-    if kind not in _GEO:
-        image, depth, mask, T = synth.edit_inputs(kind)
+    if (kind, size) not in _GEO:
+        image, depth, mask, T = synth.edit_inputs(kind, size=size)
         g = G.correspondence_field(depth.copy(), mask.copy(), T)
         amodal = G.torch_erode(G.mesh_mask(g["coords"], g["mask"])[None, None])
-        _GEO[kind] = dict(coords=g["coords"][None], mask=mask.astype(np.float32), amodal=amodal)
-    return _GEO[kind]
+        _GEO[(kind, size)] = dict(coords=g["coords"][None], mask=mask.astype(np.float32), amodal=amodal)
+    return _GEO[(kind, size)]
 
 
 def make_controller(kind, geo, cur_step, use_cfg):
@@ -179,3 +179,38 @@ def test_cross_layer_dk_split_matches_unsplit_and_fp32(N, Nk, d, M, splits):
     assert torch.equal(outs[0], outs[1])
     assert relerr(outs[0].cpu().numpy(), dk0.cpu().numpy()) <= 1e-5
     assert relerr(outs[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2
+
+
+@pytest.mark.parametrize("layout", ["heads", "proj"])
+def test_store_attention_maps(layout):
+    """`store_attention_maps` (attention_processors.py:452-454, 562-564 + attention_sharing.py:166-179): under CFG the controller keeps the edit
+    stream's attention map of every layer with N <= 16^2; the plain AttentionStore keeps the maps of the whole batch.  Values against fp32 torch."""
+    from geodiffuser_b200 import attention_processors as AP, functional as Fn
+
+    geo = geometry_for("translate2d")
+    H, d = 2, 32
+    for S, is_cross, stored in ((16, False, True), (16, True, True), (32, False, False)):
+        c = make_controller("edit", geo, 0, True)
+        c.store_attention_maps = True
+        q, k, v = (torch.from_numpy(a).cuda() for a in synth.qkv(7 + S, 4, H, S * S, 77 if is_cross else S * S, d))
+        q4, k4, v4 = q, k, v
+        if layout == "proj":
+            to_proj = lambda t: t.reshape(4, H, t.shape[1], d).permute(0, 2, 1, 3).reshape(4, t.shape[1], H * d).contiguous()
+            q4, k4, v4 = (Fn.ProjView(to_proj(t), H) for t in (q, k, v))
+        with torch.no_grad():
+            c(q4, k4, v4, is_cross, "up", transform_coords=geo["coords"], scale=d ** -0.5)
+        key = "up_cross" if is_cross else "up_self"
+        if not stored:
+            assert c.step_store[key] == []
+            continue
+        (a,) = c.step_store[key]
+        k_ref = k[3 * H:4 * H] if is_cross else k[2 * H:3 * H]       # own text keys on cross layers (:432), base keys on self layers (:555)
+        ref = torch.softmax(torch.einsum("hnd,hkd->hnk", q[3 * H:4 * H], k_ref) * d ** -0.5, -1)
+        assert a.shape == ref.shape and relerr(a.cpu().numpy(), ref.cpu().numpy()) <= TOL
+    st = AP.AttentionStore()
+    st.num_att_layers, st.batch_size = 1, 2
+    q, k, v = (torch.from_numpy(a).cuda() for a in synth.qkv(3, 2, H, 64, 64, d))
+    out = st(q, k, v, False, "mid", scale=d ** -0.5)
+    ref = torch.softmax(torch.einsum("bnd,bkd->bnk", q, k) * d ** -0.5, -1)
+    assert relerr(st.attention_store["mid_self"][0].cpu().numpy(), ref.cpu().numpy()) <= TOL
+    assert relerr(out.cpu().numpy(), (ref @ v).cpu().numpy()) <= TOL

@@ -319,3 +319,36 @@ def test_concurrent_edit_lanes_preserve_every_edit(tiny_model):
             print(f"round {round_} {k}: edited latent vs the same edit alone: PSNR {p:.1f} dB")
             assert torch.equal(o[0], alone[k][0])          # the reference sample (inversion trajectory): gradient-free graphs are bit-exact
             assert p >= 45.0
+
+
+@pytest.fixture(scope="module")
+def full_model():
+    from geodiffuser_b200 import unet_sd15
+
+    return unet_sd15.build_model("cuda")
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("body_dtype", [torch.float32, torch.bfloat16], indirect=True, ids=["fp32body", "bf16body"])
+def test_config0_full_sd15_translate2d_vs_oracle_golden(full_model, body_dtype):
+    """BASELINE.json configs[0] at FULL size: the SD-1.5 topology (8 heads, head_dim 40 / 80 / 160: the tcgen05 kernels serve the 64^2 and 32^2
+    levels), 512 x 512, 2-D translation, 5 DDIM steps, no inversion (seeded trajectory) -- against the CPU oracle loop's golden
+    (oracle/make_golden_loop.py --full: 20 minutes of CPU time).  First-pass loss and logged terms within 2e-2; final latents by PSNR."""
+    from geodiffuser_b200 import editor
+
+    z = np.load(os.path.join(GOLDEN, "loop_translate2d_full5.npz"))
+    assert int(z["meta"][0]) == 0 and int(z["meta"][1]) == 5 and int(z["meta"][2]) == 0
+    lat, log = editor.perform_synthetic_edit(full_model, "translate2d", num_ddim_steps=5, return_log=True, perform_ddim_inversion=False)
+    lat = lat.float().cpu().numpy()
+    assert np.isfinite(lat).all()
+    assert abs(log[0]["loss"] - float(z["log0_loss"])) <= 2e-2 * abs(float(z["log0_loss"])), (log[0]["loss"], float(z["log0_loss"]))
+    floor = 0.05 if body_dtype == torch.float32 else 0.15
+    for att in ("self", "cross"):
+        for k, v in log[0][att].items():
+            ref = float(z[f"log0_{att}_{k}"])
+            assert abs(v - ref) <= 2e-2 * max(abs(ref), floor), (att, k, v, ref)
+    p_ref, p_edit = psnr(lat[0], z["latents"][0]), psnr(lat[1], z["latents"][1])
+    print(f"configs[0] full SD-1.5 [{body_dtype}]: PSNR reference-branch latent {p_ref:.1f} dB, edited latent {p_edit:.1f} dB; "
+          f"loss step 0 {log[0]['loss']:.4f} / {float(z['log0_loss']):.4f}, step 2 {log[2]['loss']:.4f} / {float(z['log2_loss']):.4f}")
+    assert p_ref >= 40.0
+    assert p_edit >= (40.0 if body_dtype == torch.float32 else 25.0)

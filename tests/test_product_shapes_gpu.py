@@ -36,6 +36,9 @@ CASES = [  # name, geometry, kind, S, H, d, use_cfg, seed        (oracle/make_go
     ("remove_self_S64_H8d40_opt", "remove", "remove", 64, 8, 40, False, 203),
     ("edit_self_S32_H8d80_opt", "translate2d", "edit", 32, 8, 80, False, 204),
     ("remove_self_S32_H8d80_opt", "remove", "remove", 32, 8, 80, False, 205),
+    # BASELINE.json configs[3]: a 768 x 768 image -> first self-attention level S = 96, N = 9216 (H = 2: the reference's materialised maps);
+    # the amodal term is active here (N > 32^2)
+    ("edit_self_S96_H2d40_opt_768", "rotate3d", "edit", 96, 2, 40, False, 206),
 ]
 
 
@@ -53,7 +56,7 @@ def test_controller_at_product_shapes(case, layout):
     name, gname, kind, S, H, d, use_cfg, seed = case
     z = np.load(os.path.join(GOLDEN, f"attn_{name}.npz"))
     rows = torch.from_numpy(z["rows"].astype(np.int64)).cuda()
-    geo = geometry_for(gname)
+    geo = geometry_for(gname, 768 if name.endswith("_768") else 512)
     c = make_controller(kind, geo, 0, use_cfg)
     B = 4 if use_cfg else 2
     q, k, v = (torch.from_numpy(a).cuda() for a in synth.qkv(seed, B, H, S * S, S * S, d))
