@@ -79,6 +79,15 @@ def geometry_case(R, name, cfg):
     rec["idx512_sha"] = sha(idx512)
     rec["mask_new_warped512_sha"] = sha(mnw)
     rec["mask_new_warped512_sum"] = float(mnw.sum())
+    # the same two artefacts on the CANONICAL coords (double-accumulated centroid; what the CUDA path and the oracle compute): for rotate3d they differ
+    # from the reference's fp32-mean coords by a few ulp, so the sha above cannot be compared there -- this one can, and the count says how far apart
+    idx512_c, _, d2_c = O.splat_index(g["coords"][None])
+    mnw_c = O.binarize(O.splat_composite(mask.astype(np.float32)[None, None], idx512_c, d2_c))[0, 0]
+    rec["idx512_canonical_sha"] = sha(idx512_c)
+    rec["mask_new_warped512_canonical_sha"] = sha(mnw_c)
+    rec["idx512_mismatch_canonical_vs_reference_coords"] = int((idx512_c != idx512).sum())
+    rec["mask_new_warped512_mismatch_canonical_vs_reference_coords"] = int((mnw_c != mnw).sum())
+    print(f"     idx@512 entries differing (canonical vs reference coords): {(idx512_c != idx512).sum()}/{idx512.size}; warped-mask pixels: {(mnw_c != mnw).sum()}")
     for S in (64, 32, 16, 8):
         cS_ref = R.gt.reshape_transform_coords(tc, in_mat_shape=(1, 1, S, S))[0].numpy()
         cS = O.resize_coords(coords_ref, S)
@@ -319,6 +328,9 @@ def geometry_only(R, cfg, size=512):
 
 
 if __name__ == "__main__":
+    if "--geometry" in sys.argv:           # only the three geometry files
+        R_ = load_reference()
+        sys.exit([geometry_case(R_, n, n) for n in ("translate2d", "rotate3d", "remove")] and 0)
     if "--config3" in sys.argv:
         torch.set_grad_enabled(True)
         sys.exit(config3_case(load_reference()))

@@ -62,6 +62,11 @@ def test_mask_warp_and_amodal_bit_exact(geo, kind):
     if int(z["coords_mismatch_vs_reference"]) == 0:   # golden idx512 was built on the reference's own coords
         assert sha(g["idx512"].cpu().numpy()) == str(z["idx512_sha"])
         assert sha(g["mnw"].cpu().numpy()) == str(z["mask_new_warped512_sha"])
+    # ... and on the canonical coords (rotate3d: the reference's fp32 torch.mean centroid moves the coords by a few ulp; the golden records how
+    # many of the 512^2 x 15 index entries / warped-mask pixels that changes)
+    assert sha(g["idx512"].cpu().numpy()) == str(z["idx512_canonical_sha"])
+    assert sha(g["mnw"].cpu().numpy()) == str(z["mask_new_warped512_canonical_sha"])
+    assert int(z["mask_new_warped512_mismatch_canonical_vs_reference_coords"]) == 0
     assert float(g["mnw"].sum()) == float(z["mask_new_warped512_sum"])
     assert sha(g["amodal"].cpu().numpy()) == str(z["amodal512_sha"])
 
