@@ -286,6 +286,8 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         self._w_rem_dev = None      # device copy of loss_weight_dict[*]["removal"] (self, cross), see sync_device_weights
         self._w_rem_host = None
         self._arena = None          # editor.make_controller: per-model buffers that keep cache addresses stable across edits
+        self.base_mode = None       # None | "write" (optimisation pass stores the base sample's K / V / warped output per layer)
+        self._base_stores = {}      #                  | "read" (the CFG pass of the same timestep runs without the base sample); editor drives it
         self._log_accum = None
         self.loss_log_dict = None
         self.loss_weight_dict = None
@@ -335,6 +337,7 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         n_entries = int(self.coords_edit[1])          # the edit sample is the last batch entry (attention_processors.py:56-67)
         if q.shape[0] % n_entries == 0 and q.shape[0] // n_entries != h:
             h = q.shape[0] // n_entries               # batch without the dead unconditional reference sample (diffusion.diffusion_step)
+        base_mode = self.base_mode if (self.base_mode == "write" and not self.use_cfg) or (self.base_mode == "read" and self.use_cfg) else None
         if not (is_cross or (self.num_self_replace[0] <= self.cur_step < self.num_self_replace[1])):
             if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
                 # the reference back-propagates through compute_attention here (:646-647); the batch driver never optimises past the
@@ -356,6 +359,11 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         spec = Fn.LayerSpec(kind=self.KIND, is_cross=is_cross, heads=h, cb=tuple(self.coords_base), ce=tuple(self.coords_edit),
                             scale=float(scale), blend=self.cur_step < int(self.num_steps * self.obj_edit_step), with_loss=with_loss,
                             weights=self.loss_weight_dict[att], cache=cache, log_accum=self._log_accum[1 if is_cross else 0], w_rem_dev=w_dev)
+        if base_mode is not None:
+            # one store per attention layer (cur_att_layer walks the 32 layers in the same order in both passes); it lives with the per-model
+            # arena when there is one, so the CFG-pass graphs that read it survive across edits
+            stores = self._arena.setdefault("base_stores", {}) if self._arena is not None else self._base_stores
+            spec.base_mode, spec.base_store = base_mode, stores.setdefault((self.cur_att_layer, int(q.shape[1]), int(k.shape[1])), {})
         out, loss, _ = Fn.shared_attention_layer(q, k, v, spec)
         if N >= 32 ** 2:
             self.mask_wo_edit = cache.masks["mask_wo_edit"][None, None]
@@ -365,7 +373,7 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         if with_loss:
             self.loss = self.loss + loss
             self.loss_log_dict["num_layers"] += 1
-        if self.use_cfg and self.store_attention_maps and N <= 16 ** 2:
+        if self.use_cfg and self.store_attention_maps and N <= 16 ** 2 and base_mode != "read":
             # attention_processors.py:452-454, 562-564: the edit stream's map (edit queries against the base keys; its own text keys on cross
             # layers).  A pass that stores maps runs eagerly (graphs.edit_pass): the store is host state.
             ce, cb = int(self.coords_edit[0]), int(self.coords_base[0])

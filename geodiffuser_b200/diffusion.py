@@ -89,7 +89,7 @@ class DDIMScheduler:
 
 
 def diffusion_step(model, controller, latents, context, t, guidance_scale, low_resource=False, transform_coords=None, use_cfg=True,
-                   return_noise=False, skip_uncond_reference=False):
+                   return_noise=False, skip_uncond_reference=False, cached_reference=False):
     """diffusion.py:40-59.  With use_cfg=False the UNet runs under autograd (the caller enables grad) and the returned noise carries
     the graph; the latent step itself is never differentiated by the reference loop (only controller.loss is, editor.py:273).
 
@@ -99,7 +99,18 @@ def diffusion_step(model, controller, latents, context, t, guidance_scale, low_r
     [uncond edit, cond ref, cond edit] (controller coords (1,2) / (2,3)) and latents_out[0] is returned unchanged for the caller to overwrite.
     The edited sample's result is identical."""
     with body_autocast():
-        if use_cfg and skip_uncond_reference:
+        if use_cfg and cached_reference:
+            # SURVEY 8(f) N4: the optimisation pass of this timestep has just evaluated the conditional reference sample and the controller has kept
+            # what the edit needs from it (base K / V, warped-stream output per layer: controller.base_mode == "read").  The UNet sees only
+            # [uncond edit, cond edit]; latents_out[0] is returned unchanged for the caller to overwrite (editor.py:375-377).
+            from . import graphs
+
+            assert latents.shape[0] == 2 and context.shape[0] == 4 and not return_noise and controller.base_mode == "read"
+            noise_pred = graphs.edit_pass(model, controller, torch.cat([latents[1:], latents[1:]]), t, context[[1, 3]])
+            latents_out = latents.detach().float().clone()
+            latents_out[1:] = model.scheduler.step_cfg(noise_pred[0:1], noise_pred[1:2], guidance_scale, t, latents[1:])
+            noise_pred_out = None
+        elif use_cfg and skip_uncond_reference:
             from . import graphs
 
             assert latents.shape[0] == 2 and context.shape[0] == 4 and not return_noise

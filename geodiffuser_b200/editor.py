@@ -21,6 +21,8 @@ NUM_DDIM_STEPS = 50
 IMAGE_SIZE = 512
 SEED = 1234  # editor.py:47
 SKIP_DEAD_UNCOND_REFERENCE = True   # diffusion.diffusion_step(skip_uncond_reference=...): result-preserving, 1/4 of every CFG pass
+REUSE_REFERENCE_OF_OPT_PASS = True  # on a timestep with an optimisation pass, the CFG pass reuses the reference sample's per-layer
+                                    # K / V / warped-stream output from that pass instead of re-evaluating the sample (1/3 of those CFG passes)
 
 
 def clear_controller_loss(controller):
@@ -102,6 +104,8 @@ def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, gui
             best_loss, best_latents, best_context = 1e8, None, None
             l_eff = lr * (50 - i) * skip_optim_steps * (50 / (NUM_DDIM_STEPS + 1e-8))  # editor.py:207
             set_attn_processor_for_edit(model, coords_base=(0, 1), coords_edit=(1, 2), use_cfg=False)
+            reuse = REUSE_REFERENCE_OF_OPT_PASS and SKIP_DEAD_UNCOND_REFERENCE and ddim_latents is not None and hasattr(controller, "base_mode")
+            controller.base_mode = "write" if reuse else None
             latents_in = latents.detach().float().requires_grad_(True)
             orig_norm = norm_tensor_dev(latents_in[-1:].detach())   # stays on the device (no host sync in front of the optimisation pass)
             context_in = (context if context_save is None else context_save).detach().float().requires_grad_(True)
@@ -140,13 +144,21 @@ def text2image_ldm_stable(model, prompt, controller, num_inference_steps=50, gui
             context = context_save
         # the reference latent is overwritten below whenever the inversion trajectory is given, which makes its unconditional evaluation dead work
         skip = SKIP_DEAD_UNCOND_REFERENCE and ddim_latents is not None
-        if skip:
+        # the reference sample of this timestep was evaluated by the optimisation pass above (same latent, same conditional context): reuse it
+        cached = do_opt and getattr(controller, "base_mode", None) == "write"
+        if hasattr(controller, "base_mode"):
+            controller.base_mode = "read" if cached else None
+        if cached:
+            set_attn_processor_for_edit(model, coords_base=(0, 1), coords_edit=(1, 2), use_cfg=True)     # batch [uncond edit, cond edit]
+        elif skip:
             set_attn_processor_for_edit(model, coords_base=(1, 2), coords_edit=(2, 3), use_cfg=True)
         else:
             set_attn_processor_for_edit(model, coords_base=(2, 3), coords_edit=(3, 4), use_cfg=True)
         if not i < fast_start_steps * n_t:
             latents = diffusion_step(model, controller, latents, context, t, guidance_scale, transform_coords=transform_coordinates,
-                                     skip_uncond_reference=skip)
+                                     skip_uncond_reference=skip, cached_reference=cached)
+        if hasattr(controller, "base_mode"):
+            controller.base_mode = None
         if ddim_latents is not None:
             i_n = len(ddim_latents) - 2 - i
             latents = torch.cat([ddim_latents[i_n].to(latents), latents[-1:].detach()], 0)  # editor.py:375-377

@@ -19,7 +19,10 @@ import torch
 from . import _lib
 
 _CAPTURE_LOCK = threading.RLock()   # one capture at a time per process: the garbage collector is paused around it (runner.EditWorkers runs
-                                    # several edits of one GPU from several threads)
+                                    # several edits of one GPU from several threads).  EAGER evaluations of the body take it as well: that is
+                                    # where cuDNN autotunes (torch.backends.cudnn.benchmark), and its timing runs (device synchronisation,
+                                    # allocations) abort a capture in progress on another thread -- CUDNN_STATUS_INTERNAL_ERROR /
+                                    # cudaErrorStreamCaptureInvalidated.  Replays never take it.
 ENABLED = True      # product default; tests compare against the eager path by switching it off
 GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as well
 CAPTURE_ERROR_MODE = "thread_local"   # cudaStreamCaptureMode of the hand-driven captures: CUDA calls that OTHER threads make meanwhile (another
@@ -102,7 +105,8 @@ class GraphedUNet:
             if self.warmup_left > 0 or tid not in self.warm_threads:
                 self.warmup_left = max(0, self.warmup_left - 1)
                 self.warm_threads.add(tid)
-                return self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
+                with _CAPTURE_LOCK:
+                    return self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
             g = torch.cuda.CUDAGraph()
             l0, f0 = _lib.LAUNCHES, _lib.FLOPS
             with _capture(g, self.pool, self.stream):
@@ -120,7 +124,7 @@ def controller_key(controller):
     """the controller state a captured edit pass depends on"""
     c = controller
     return (bool(c.use_cfg), tuple(c.coords_base), tuple(c.coords_edit), c.num_self_replace[0] <= c.cur_step < c.num_self_replace[1],
-            c.cur_step < int(c.num_steps * c.obj_edit_step))
+            c.cur_step < int(c.num_steps * c.obj_edit_step), getattr(c, "base_mode", None))
 
 
 def edit_pass(model, controller, latents_input, t, context):
@@ -129,7 +133,8 @@ def edit_pass(model, controller, latents_input, t, context):
     # a graph captured for an earlier edit may only be replayed once THIS controller has refreshed the shared cache buffers, i.e. after its
     # first real evaluation (normally the first optimisation pass)
     if not ENABLED or torch.is_grad_enabled() or getattr(controller, "eager_passes", 0) == 0 or getattr(controller, "store_attention_maps", False):
-        return model.unet(latents_input, t, encoder_hidden_states=context)["sample"]
+        with _CAPTURE_LOCK:
+            return model.unet(latents_input, t, encoder_hidden_states=context)["sample"]
     store = controller.__dict__.setdefault("_unet_graphs", {})
     arena = controller.__dict__.get("_arena")
     key = (controller_key(controller), tuple(latents_input.shape), id(model.unet), arena.get("generation", 0) if arena is not None else -1)
@@ -148,7 +153,8 @@ def inversion_pass(model, latents_input, t, context):
     """One UNet evaluation of the DDIM inversion (vanilla attention, no controller state): the graph lives on the model and is reused by
     every step of every edit."""
     if not ENABLED or torch.is_grad_enabled():
-        return model.unet(latents_input, t, encoder_hidden_states=context)["sample"]
+        with _CAPTURE_LOCK:
+            return model.unet(latents_input, t, encoder_hidden_states=context)["sample"]
     store = model.__dict__.setdefault("_inversion_graphs", {})
     key = (tuple(latents_input.shape), tuple(context.shape), id(model.unet))
     g = store.get(key)
@@ -235,9 +241,11 @@ def grad_pass(model, controller, latents, context, t):
     dev = latents.device
 
     def eager():
-        with torch.enable_grad():
+        with _CAPTURE_LOCK, torch.enable_grad():
             model.unet(latents, t, encoder_hidden_states=context[context.shape[0] // 2:])
             g = torch.autograd.grad(controller.loss, [latents, context], allow_unused=True)
+            if len(threading.enumerate()) > 1:
+                torch.cuda.current_stream(dev).synchronize()     # the backward's autotune runs on the autograd thread: let it finish under the lock
         return g
 
     if not (ENABLED and GRAD_ENABLED) or not latents.is_cuda:

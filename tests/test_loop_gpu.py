@@ -352,3 +352,34 @@ def test_config0_full_sd15_translate2d_vs_oracle_golden(full_model, body_dtype):
           f"loss step 0 {log[0]['loss']:.4f} / {float(z['log0_loss']):.4f}, step 2 {log[2]['loss']:.4f} / {float(z['log2_loss']):.4f}")
     assert p_ref >= 40.0
     assert p_edit >= (40.0 if body_dtype == torch.float32 else 25.0)
+
+
+@pytest.mark.parametrize("kind", ["rotate3d", "remove"])
+def test_reference_reuse_between_optimisation_and_cfg_pass(tiny_model, kind):
+    """SURVEY 8(f) N4, second half (editor.REUSE_REFERENCE_OF_OPT_PASS): on a timestep with an optimisation pass the CFG pass runs without the
+    reference sample -- batch [uncond edit, cond edit], G = 2 attention streams -- and takes the base K / V and the warped-stream output of every
+    layer from that optimisation pass (same latent, same timestep, same conditional context: editor.py:253 vs :351).  Mathematically the same
+    edit; numerically the reference sample's activations come from a batch-2 instead of a batch-3 evaluation of the body, so equality is up to
+    the body's batch-size-dependent rounding (fp32 body here: the path's own arithmetic is identical)."""
+    from geodiffuser_b200 import diffusion, editor, _lib
+
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    diffusion.set_body_dtype(torch.float32)
+    try:
+        res, flops = {}, {}
+        for reuse in (False, True):
+            editor.REUSE_REFERENCE_OF_OPT_PASS = reuse
+            editor.perform_synthetic_edit(tiny_model, kind, num_ddim_steps=8)          # (graphs captured)
+            f0 = _lib.FLOPS
+            res[reuse] = editor.perform_synthetic_edit(tiny_model, kind, num_ddim_steps=8).float().cpu()
+            flops[reuse] = _lib.FLOPS - f0
+    finally:
+        editor.REUSE_REFERENCE_OF_OPT_PASS = True
+        diffusion.set_body_dtype(torch.bfloat16)
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert torch.equal(res[True][0], res[False][0])
+    p = psnr(res[True][1].numpy(), res[False][1].numpy())
+    print(f"{kind}: edited latent with the reference reused vs recomputed: PSNR {p:.1f} dB; attention-path FLOP per edit {flops[False]:.3e} -> {flops[True]:.3e}")
+    assert p >= 50.0
+    assert flops[True] < flops[False]
