@@ -153,18 +153,18 @@ if only in ("corr", "sweep"):
     corr_case(8, 1024, 80, 100)
 
 if only == "sweep":
-    for np_ in (-1, 0, 2, 3):
+    for stream_, np_ in ((0, 2), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4)):
+        cfg(4, stream_)
         cfg(0, np_)
-        print(f"--- fwd: {'round-1 scalar arithmetic, poly=4' if np_ < 0 else f'packed arithmetic, {np_}/8 pairs on the polynomial'}", flush=True)
+        print(f"--- fwd: {'chunk-streaming' if stream_ else 'whole-tile'} softmax, {np_}/8 pairs on the polynomial", flush=True)
         fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
         fwd_case("gd_attn_fwd_sm100", 4, 8, 4096, 40)
         fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
         fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
+    cfg(4, 1)
     cfg(0, 2)
-    cfg(0, 2)
-    for variant, nps in ((0, (0,)), (1, (1,))):
+    for variant, nps in ((1, (0, 1)),):
         for np_ in nps:
-            cfg(2, variant)
             cfg(3, np_)
             print(f"--- bwd: variant {variant} ({'128-key steps, 1 CTA/SM' if variant == 0 else f'64-key steps, 2 CTA/SM, {np_}/8 pairs on the polynomial'})", flush=True)
             bwd_case(8, 4096, 40, sm100=True)
@@ -172,7 +172,6 @@ if only == "sweep":
             bwd_case(8, 1024, 80, sm100=True)
             bwd_case(8, 1024, 80, M=100, sm100=True)
             bwd_case(2, 9216, 40, sm100=True)
-    cfg(2, 1)
     cfg(3, 0)
 if only in (None, "fwd"):
     fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)

@@ -170,3 +170,33 @@ def test_projection_layout_is_read_and_written_in_place(N, Nk, d, H):
     assert torch.equal(res["proj"][0], unperm(res["heads"][0])) and float(res["proj"][0][1].abs().max()) > 0
     assert float(res["proj"][0][0].abs().max()) == 0.0
     assert torch.equal(res["proj"][1], unperm(res["heads"][1])) and float(res["proj"][1][1].abs().max()) > 0
+
+
+@pytest.mark.parametrize("d", [40, 80])
+@pytest.mark.parametrize("pattern", ["staircase", "ramp_then_flat", "spike"])
+def test_forward_reference_moves_inside_a_tile(d, pattern):
+    """The streaming softmax updates its reference per 32-column chunk, lazily (growth > 2^8); when a row's reference moves INSIDE a 128-key
+    tile the chunks already written are recomputed from S.  Adversarial score profiles force that path: a staircase rising by ~17 nats
+    every 16 keys (growth in every chunk of every tile), a ramp that stops, one spike in the middle of a tile.  Against fp32 torch."""
+    from geodiffuser_b200 import functional as Fn
+
+    H, N = 2, 1024
+    g = torch.Generator(device="cuda").manual_seed(d + len(pattern))
+    u = torch.nn.functional.normalize(torch.randn(d, device="cuda", generator=g), dim=0)
+    n = torch.arange(N, device="cuda", dtype=torch.float32)
+    if pattern == "staircase":
+        prof = torch.floor(n / 16) * 2.5
+    elif pattern == "ramp_then_flat":
+        prof = torch.clamp(n * 0.4, max=120.0)
+    else:
+        prof = torch.zeros(N, device="cuda"); prof[N // 2 + 37] = 90.0
+    k = (prof[:, None] * u[None, :] + 0.3 * torch.randn(N, d, device="cuda", generator=g))[None].repeat(H, 1, 1).bfloat16()
+    q = ((d ** 0.5) * 0.5 * u[None, :] + 0.3 * torch.randn(N, d, device="cuda", generator=g))[None].repeat(H, 1, 1).bfloat16()
+    v = torch.randn(H, N, d, device="cuda", generator=g).bfloat16()
+    scale = d ** -0.5
+    O, LSE = Fn.attention_forward([q], [k], [v], scale)
+    s = torch.einsum("hnd,hkd->hnk", q.float(), k.float()) * scale
+    ref = torch.softmax(s, -1) @ v.float()
+    assert torch.isfinite(O[0]).all() and torch.isfinite(LSE[0]).all()
+    assert relerr(O[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2
+    assert relerr(LSE[0].cpu().numpy(), torch.logsumexp(s, -1).cpu().numpy()) <= 1e-3
