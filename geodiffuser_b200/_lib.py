@@ -5,6 +5,7 @@ PyTorch is used by the callers only for device memory, streams and autograd plum
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -60,7 +61,53 @@ SIGNATURES = {
 
 _LIB = None
 HAS_SM100 = "gd_attn_fwd_sm100" in SIGNATURES
-LAUNCHES = 0  # CUDA kernels launched through the C ABI by this process (bench.py reports it as gpu_launches)
+
+
+class _Counters:
+    """per host thread (runner.EditWorkers drives several edits of one GPU from several threads): kernels launched through the C ABI and their
+    algorithmic attention-path FLOP.  `_lib.LAUNCHES` / `_lib.FLOPS` read the sum over all threads (bench.py: gpu_launches, edit-level roofline)."""
+    __slots__ = ("launches", "flops")
+
+    def __init__(self):
+        self.launches, self.flops = 0, 0.0
+
+
+_TLS = threading.local()
+_ALL_COUNTERS = []
+
+
+def counters():
+    c = getattr(_TLS, "override", None) or getattr(_TLS, "c", None)
+    if c is None:
+        c = _TLS.c = _Counters()
+        _ALL_COUNTERS.append(c)
+    return c
+
+
+class count_into:
+    """`with count_into(c):` -- launches made by this thread are booked on the counters `c` of another thread.  The backward of the fused layer
+    runs on autograd's device thread; it books its launches on the thread that ran the forward (the edit lane), which is the one that records and
+    replays the optimisation-pass graph (graphs.GraphedGradPass)."""
+
+    def __init__(self, c):
+        self.c = c
+
+    def __enter__(self):
+        self.prev = getattr(_TLS, "override", None)
+        _TLS.override = self.c
+
+    def __exit__(self, *exc):
+        _TLS.override = self.prev
+
+
+def __getattr__(name):      # module attribute access: the process-wide totals
+    if name == "LAUNCHES":
+        return sum(c.launches for c in _ALL_COUNTERS)
+    if name == "FLOPS":
+        return sum(c.flops for c in _ALL_COUNTERS)
+    raise AttributeError(name)
+
+
 KERNELS_PER_CALL = {"gd_attn_sm100_config": 0, "gd_corr_pixel2cam": 2, "gd_removal_finalize": 1, "gd_amodal_target": 2, "gd_attn_bwd_dk_split": 2,
                     "gd_group_norm_nhwc_fwd": 1, "gd_group_norm_nhwc_bwd": 2, "gd_group_norm_nhwc_workspace": 0, "gd_group_norm_config": 0, "gd_masked_histogram_match": 3}  # every other entry point launches one
 
@@ -107,9 +154,6 @@ def profile_end():
     return out
 
 
-FLOPS = 0.0  # algorithmic FLOP of the attention-path contractions launched by this process (SURVEY 8(d) formulas; bench.py: share of the roofline)
-
-
 def algorithmic_flops(name, tag):
     """forward 4*G*H*N*Nk*d (QK^T + PV per stream), backward 6*H*N*Nk*d (recompute S, dP, dQ or dK), removal correlation
     2*H*M*N*Nk.  `tag` = the shape tuple the caller passes with the launch."""
@@ -128,10 +172,10 @@ def algorithmic_flops(name, tag):
 
 
 def call(name, *args, tag=None):
-    global LAUNCHES, FLOPS
     L_ = lib()
+    cnt = counters()
     if tag is not None:
-        FLOPS += algorithmic_flops(name, tag)
+        cnt.flops += algorithmic_flops(name, tag)
     if PROFILE is not None and name in PROFILE["names"] and not torch.cuda.is_current_stream_capturing():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -140,7 +184,7 @@ def call(name, *args, tag=None):
         PROFILE["events"].append((name, tag, e0, e1))
     else:
         rc = getattr(L_, name)(*args)
-    LAUNCHES += KERNELS_PER_CALL.get(name, 1)
+    cnt.launches += KERNELS_PER_CALL.get(name, 1)
     if rc != 0:
         raise GeoDiffuserB200Error(f"{name} failed with status {rc}: {L_.gd_last_error().decode()}")
 

@@ -406,6 +406,7 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
     def forward(ctx, q, k, v, spec, proj):
         out, terms, saved = _forward_impl(q, k, v, spec, proj)
         ctx.spec, ctx.saved_dict = spec, saved
+        ctx.counters = _lib.counters()
         ctx.shapes = (q.shape, k.shape, q.dtype, k.dtype)
         if terms is None:
             terms = torch.zeros(6, device=q.device, dtype=torch.float32)
@@ -414,6 +415,11 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, d_out, d_terms):
+        with _lib.count_into(ctx.counters):
+            return _SharedAttentionLayerFn._backward(ctx, d_out, d_terms)
+
+    @staticmethod
+    def _backward(ctx, d_out, d_terms):
         spec, s = ctx.spec, ctx.saved_dict
         h, (cb0, cb1), (ce0, ce1) = spec.heads, spec.cb, spec.ce
         q_shape, k_shape, q_dtype, k_dtype = ctx.shapes

@@ -108,15 +108,17 @@ class GraphedUNet:
                 with _CAPTURE_LOCK:
                     return self.unet(self.sample, self.t, encoder_hidden_states=self.context)["sample"]
             g = torch.cuda.CUDAGraph()
-            l0, f0 = _lib.LAUNCHES, _lib.FLOPS
+            cnt = _lib.counters()                       # (this thread's: a capture is recorded by one thread)
+            l0, f0 = cnt.launches, cnt.flops
             with _capture(g, self.pool, self.stream):
                 self.out = self._eval()
-            self.path_launches, self.path_flops = _lib.LAUNCHES - l0, _lib.FLOPS - f0
-            _lib.LAUNCHES, _lib.FLOPS = l0, f0          # capturing launches nothing
+            self.path_launches, self.path_flops = cnt.launches - l0, cnt.flops - f0
+            cnt.launches, cnt.flops = l0, f0            # capturing launches nothing
             self.graph = g
         self.graph.replay()
-        _lib.LAUNCHES += self.path_launches
-        _lib.FLOPS += self.path_flops
+        cnt = _lib.counters()
+        cnt.launches += self.path_launches
+        cnt.flops += self.path_flops
         return self.out
 
 
@@ -195,17 +197,20 @@ class GraphedGradPass:
         if self.graph is None:
             g = torch.cuda.CUDAGraph()
             step, layers = c.cur_step, c.loss_log_dict["num_layers"]
-            l0, f0 = _lib.LAUNCHES, _lib.FLOPS
+            cnt = _lib.counters()
+            l0, f0 = cnt.launches, cnt.flops
             with _capture(g, _pool(self.model), _side_stream(self.model, latents.device), sync=self.sync):
                 self.loss, self.g_lat, self.g_ctx = self._run(c)
-            self.path_launches, _lib.LAUNCHES = _lib.LAUNCHES - l0, l0
-            self.path_flops, _lib.FLOPS = _lib.FLOPS - f0, f0
+            # (the layers' backward launches run on the autograd thread and are counted there: add that thread's share of this capture)
+            self.path_launches, cnt.launches = cnt.launches - l0, l0
+            self.path_flops, cnt.flops = cnt.flops - f0, f0
             self.num_layers = c.loss_log_dict["num_layers"] - layers
             c.cur_step, c.loss_log_dict["num_layers"] = step, layers
             self.graph = g
         self.graph.replay()
-        _lib.LAUNCHES += self.path_launches
-        _lib.FLOPS += self.path_flops
+        cnt = _lib.counters()
+        cnt.launches += self.path_launches
+        cnt.flops += self.path_flops
         c.loss = self.loss
         c.cur_step += 1
         c.loss_log_dict["num_layers"] += self.num_layers
