@@ -42,9 +42,7 @@ struct Sm100Params {
 // D = head_dim (40 or 80).  KB = number of 64-wide (128-byte) column blocks per operand row; KSTEPS = ceil(D/16); DV = O columns.
 // NP >= 0 (the product path): packed fp32x2 softmax arithmetic, NP of every 8 score pairs on the FMA-pipe polynomial, the rest on the MUFU.
 // NP < 0 (round-1 arithmetic, kept for A/B measurements): scalar ops, POLY = every POLY-th exponential on the polynomial (0 = none).
-// STREAM = 1: the softmax warps walk a score tile in four 32-column chunks that are loaded from TMEM one chunk ahead (tcgen05.ld of chunk c+1 under
-// the exponentials of chunk c) instead of holding all 128 scores in registers behind a full-row max; the softmax reference is updated per chunk.
-template <int D, int POLY, int NP, int STREAM>
+template <int D, int POLY, int NP>
 __global__ void __launch_bounds__(SM100_THREADS, (D <= 64) ? 2 : 1)
 attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params p) {
     constexpr int KB = (D + 63) / 64;
@@ -156,116 +154,6 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         const float scale2 = p.scale2;
         float m_run = -INFINITY, l_run = 0.f;
-        if constexpr (STREAM != 0) {
-            // ---- streaming form ----------------------------------------------------------------------------------------------------
-            // Per 32-column chunk: wait for its tcgen05.ld, request the next chunk, chunk max (FMNMX3 tree), lazy reference update, exponentials,
-            // bf16 P chunk -> TMEM.  Registers: two 32-score buffers instead of 128 live scores (the scheduler window of the first form was
-            // short: 31 % of its arithmetic cycles were fixed-latency dependency stalls), no full-row max in front of the first exponential.
-            // The reference m of a row may GROW inside a tile (by more than 2^8, the lazy threshold): the P chunks of this tile written under
-            // the old reference are then recomputed from S, which stays in TMEM until the last chunk has been checked (s_free arrives there);
-            // O and the running sum are corrected once per tile, before P(j) is handed to the PV product.
-            const u64 sc2 = pk2(scale2, scale2);
-            auto exp_chunk = [&](const uint32_t* sr, float m_ref, uint32_t* pk, u64& rsA, u64& rsB) {
-                const u64 nm2 = pk2(-m_ref, -m_ref);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    const u64 x2 = fma2(pk2u(sr[2 * c], sr[2 * c + 1]), sc2, nm2);
-                    u64 p2;
-                    float p0, p1;
-                    if (pair_is_poly<NP>(c)) {
-                        p2 = ex2_poly2(x2);
-                        upk2(p2, p0, p1);
-                    } else {
-                        float x0, x1;
-                        upk2(x2, x0, x1);
-                        p0 = ex2(x0);
-                        p1 = ex2(x1);
-                        p2 = pk2(p0, p1);
-                    }
-                    if (c & 1) rsB = add2(rsB, p2); else rsA = add2(rsA, p2);
-                    __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-                    pk[c] = *reinterpret_cast<uint32_t*>(&b2);
-                }
-            };
-            for (int j = 0; j < nT; ++j) {
-                mbar_wait(s_full, j & 1);
-                tc_fence_after();
-                uint32_t buf[2][32];
-                tmem_ld32(tmem + lane_off + COL_S, buf[0]);
-                const float m_start = m_run;
-                float m_ref = m_run, l_tile = 0.f;
-#pragma unroll
-                for (int cc = 0; cc < BN / 32; ++cc) {
-                    uint32_t* sr = buf[cc & 1];
-                    tmem_wait_ld();                                              // chunk cc has landed
-                    if (cc + 1 < BN / 32) tmem_ld32(tmem + lane_off + COL_S + (cc + 1) * 32, buf[(cc + 1) & 1]);
-                    float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
-#pragma unroll
-                    for (int c = 0; c < 32; c += 8) {
-                        mx0 = max3(mx0, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
-                        mx1 = max3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
-                        mx2 = max3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
-                        mx3 = max3(mx3, __uint_as_float(sr[c + 6]), __uint_as_float(sr[c + 7]));
-                    }
-                    const float m_cand = fmaxf(m_ref, fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale2);
-                    const bool grow = (m_cand - m_ref) > 8.0f;
-                    if (cc > 0 && __any_sync(0xffffffffu, grow)) {
-                        // rare: the reference of some row of this warp moved inside the tile.  Rows that grew rescale their tile sum and redo
-                        // their earlier chunks under the new reference (the others redo them under the old one: same values again).
-                        const float m_new = grow ? m_cand : m_ref;
-                        l_tile *= ex2(m_ref - m_new);
-                        if (cc + 1 < BN / 32) tmem_wait_ld();                    // the prefetch must land before its buffer is the only copy in flight
-                        if (j > 0) { mbar_wait(pv_done, (j - 1) & 1); tc_fence_after(); }
-                        for (int r = 0; r < cc; ++r) {
-                            uint32_t tmp[32], pk[16];
-                            tmem_ld32(tmem + lane_off + COL_S + r * 32, tmp);
-                            tmem_wait_ld();
-                            u64 dA = 0ull, dB = 0ull;                            // (sums of the redone chunks are already in l_tile, rescaled)
-                            exp_chunk(tmp, m_new, pk, dA, dB);
-                            tmem_st16(tmem + lane_off + COL_P + r * 16, pk);
-                        }
-                        m_ref = m_new;
-                    } else if (grow) {
-                        m_ref = m_cand;                                          // first chunk of the tile: nothing written under the old reference yet
-                        // (l_tile is still 0)
-                    }
-                    if (cc + 1 == BN / 32) {
-                        tc_fence_before();
-                        if (lane == 0) mbar_arrive(s_free);                      // every chunk of S(j) has been read and checked: QK^T(j+1) may overwrite it
-                    }
-                    uint32_t pk[16];
-                    u64 rsA = 0ull, rsB = 0ull;
-                    exp_chunk(sr, m_ref, pk, rsA, rsB);
-                    float a0, a1;
-                    upk2(add2(rsA, rsB), a0, a1);
-                    l_tile += a0 + a1;
-                    if (cc == 0 && j > 0) {
-                        mbar_wait(pv_done, (j - 1) & 1);                         // P(j) may overwrite P(j-1) only once PV(j-1) has completed
-                        tc_fence_after();
-                    }
-                    tmem_st16(tmem + lane_off + COL_P + cc * 16, pk);
-                }
-                // once per tile: bring O and the running sum to the tile's final reference
-                const bool grown = m_ref != m_start;
-                const float alpha = grown ? ex2(m_start - m_ref) : 1.0f;
-                if (j > 0 && __any_sync(0xffffffffu, grown)) {
-#pragma unroll
-                    for (int c = 0; c < DV / 16; ++c) {
-                        uint32_t orr[16];
-                        tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
-                        tmem_st16(tmem + lane_off + COL_O + c * 16, orr);
-                    }
-                }
-                l_run = l_run * alpha + l_tile;
-                m_run = m_ref;
-                tmem_wait_st();
-                tc_fence_before();
-                if (lane == 0) mbar_arrive(p_full);
-            }
-        } else
         for (int j = 0; j < nT; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
@@ -702,41 +590,33 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
 // ---- host side -------------------------------------------------------------------------------------------------------------
 static int g_poly = 4;   // round-1 arithmetic only (g_np < 0): every g_poly-th exponential goes to the FMA pipe
 static int g_bwd_np = 0;
-static int g_fwd_stream = 1;   // forward softmax: 1 = chunk-streaming form, 0 = whole tile in registers behind a full-row max
 static int g_np = 2;     // tuning knob (gd_attn_sm100_config): packed arithmetic, g_np of every 8 score pairs on the FMA-pipe polynomial
 
-template <int D, int POLY, int NP, int STREAM> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
+template <int D, int POLY, int NP> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
     constexpr int KB = (D + 63) / 64;
     const size_t smem = (size_t)5 * KB * 128 * 128 + 256 + 1024;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D, POLY, NP, STREAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D, POLY, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     dim3 grid(p.N / BM, p.H, G);
-    attn_fwd_sm100_kernel<D, POLY, NP, STREAM><<<grid, SM100_THREADS, smem, st>>>(maps, p);
+    attn_fwd_sm100_kernel<D, POLY, NP><<<grid, SM100_THREADS, smem, st>>>(maps, p);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }
 
 template <int D> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
-    if (g_fwd_stream) {
-        switch (g_np) {
-            case 0: return launch_sm100<D, 0, 0, 1>(maps, p, G, st);
-            case 1: return launch_sm100<D, 0, 1, 1>(maps, p, G, st);
-            case 2: return launch_sm100<D, 0, 2, 1>(maps, p, G, st);
-            case 3: return launch_sm100<D, 0, 3, 1>(maps, p, G, st);
-            case 4: return launch_sm100<D, 0, 4, 1>(maps, p, G, st);
-        }
-    }
     switch (g_np) {
-        case 0: return launch_sm100<D, 0, 0, 0>(maps, p, G, st);
-        case 2: return launch_sm100<D, 0, 2, 0>(maps, p, G, st);
-        case 3: return launch_sm100<D, 0, 3, 0>(maps, p, G, st);
+        case 0: return launch_sm100<D, 0, 0>(maps, p, G, st);
+        case 1: return launch_sm100<D, 0, 1>(maps, p, G, st);
+        case 2: return launch_sm100<D, 0, 2>(maps, p, G, st);
+        case 3: return launch_sm100<D, 0, 3>(maps, p, G, st);
+        case 4: return launch_sm100<D, 0, 4>(maps, p, G, st);
     }
-    if (g_np < 0 && g_poly == 4) return launch_sm100<D, 4, -1, 0>(maps, p, G, st);
-    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for poly=%d np=%d stream=%d", g_poly, g_np, g_fwd_stream);
+    if (g_np < 0 && g_poly == 4) return launch_sm100<D, 4, -1>(maps, p, G, st);
+    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for poly=%d np=%d", g_poly, g_np);
 }
 
 template <int D, int NP> static int launch_bwd64_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
@@ -800,14 +680,12 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
 //   key 0  fwd: packed fp32x2 softmax arithmetic with `value` in 0..4 of every 8 score pairs on the FMA-pipe polynomial (default 2);
 //               value -1 selects the round-1 scalar arithmetic (A/B measurements), whose polynomial share is key 1
 //   key 1  fwd, scalar arithmetic only: every value-th exponential on the polynomial, value in {0, 4}
-//   key 4  fwd: 1 = chunk-streaming softmax (default), 0 = whole score tile in registers behind a full-row max (keys 0 in {0,2,3} or -1)
 //   key 3  bwd: value in 0..4 of every 8 score pairs on the polynomial (default 0)
 extern "C" int gd_attn_sm100_config(int key, int value) {
     switch (key) {
         case 0: if (value < -1 || value > 4) break; g_np = value; return GD_OK;
         case 1: if (value != 4) break; g_poly = value; return GD_OK;
         case 3: if (value < 0 || value > 4) break; g_bwd_np = value; return GD_OK;
-        case 4: if (value < 0 || value > 1) break; g_fwd_stream = value; return GD_OK;
     }
     return set_error(GD_ERR_INVALID, "gd_attn_sm100_config(key=%d, value=%d): see include/geodiffuser_b200.h", key, value);
 }

@@ -153,15 +153,13 @@ if only in ("corr", "sweep"):
     corr_case(8, 1024, 80, 100)
 
 if only == "sweep":
-    for stream_, np_ in ((0, 2), (1, 0), (1, 1), (1, 2), (1, 3), (1, 4)):
-        cfg(4, stream_)
+    for np_ in (-1, 0, 1, 2, 3, 4):
         cfg(0, np_)
-        print(f"--- fwd: {'chunk-streaming' if stream_ else 'whole-tile'} softmax, {np_}/8 pairs on the polynomial", flush=True)
+        print(f"--- fwd: {'round-1 scalar arithmetic, every 4th exponential on the polynomial' if np_ < 0 else f'packed arithmetic, {np_}/8 pairs on the polynomial'}", flush=True)
         fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
         fwd_case("gd_attn_fwd_sm100", 4, 8, 4096, 40)
         fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
         fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
-    cfg(4, 1)
     cfg(0, 2)
     for variant, nps in ((1, (0, 1)),):
         for np_ in nps:

@@ -175,9 +175,8 @@ def test_projection_layout_is_read_and_written_in_place(N, Nk, d, H):
 @pytest.mark.parametrize("d", [40, 80])
 @pytest.mark.parametrize("pattern", ["staircase", "ramp_then_flat", "spike"])
 def test_forward_reference_moves_inside_a_tile(d, pattern):
-    """The streaming softmax updates its reference per 32-column chunk, lazily (growth > 2^8); when a row's reference moves INSIDE a 128-key
-    tile the chunks already written are recomputed from S.  Adversarial score profiles force that path: a staircase rising by ~17 nats
-    every 16 keys (growth in every chunk of every tile), a ramp that stops, one spike in the middle of a tile.  Against fp32 torch."""
+    """The online softmax rescales O lazily (only when a row's running max grows by more than 2^8).  Adversarial score profiles exercise that
+    path on every tile: a staircase rising by ~17 nats every 16 keys, a ramp that stops, one spike in the middle of a tile.  Against fp32 torch."""
     from geodiffuser_b200 import functional as Fn
 
     H, N = 2, 1024
