@@ -30,7 +30,7 @@ N_OPT, N_CFG, N_INV = 17, 50, 50   # UNet passes per edit with the perform_exp h
 
 def bench_config(n):
     """the same dict in both arms (the driver compares them)"""
-    return {"workload": WORKLOAD, "parallelism": f"request-level dp{n} (independent edits, no collective; 2 edit lanes per GPU in the GPU arm)",
+    return {"workload": WORKLOAD, "parallelism": f"request-level dp{n} (independent edits, no collective; 3 edit lanes per GPU in the GPU arm)",
             "l2": "no flush needed: every UNet pass streams 1.7 GB of weights + activations (> 126 MB L2) between repeats"}
 
 
@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="config1", choices=["config1", "mixed64"],
                     help="config1 = BASELINE configs[1] (the metric's configuration); mixed64 = configs[4], the 64-edit mixed sweep")
-    ap.add_argument("--lanes", type=int, default=2, help="independent edits in flight per GPU (1 = one edit at a time)")
+    ap.add_argument("--lanes", type=int, default=3, help="independent edits in flight per GPU (1 = one edit at a time)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

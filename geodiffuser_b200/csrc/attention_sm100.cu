@@ -589,7 +589,7 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
 static int g_poly = 4;   // round-1 arithmetic only (g_np < 0): every g_poly-th exponential goes to the FMA pipe
-static int g_bwd_np = 0;
+static int g_bwd_np = 1;
 static int g_np = 2;     // tuning knob (gd_attn_sm100_config): packed arithmetic, g_np of every 8 score pairs on the FMA-pipe polynomial
 
 template <int D, int POLY, int NP> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
@@ -680,7 +680,7 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
 //   key 0  fwd: packed fp32x2 softmax arithmetic with `value` in 0..4 of every 8 score pairs on the FMA-pipe polynomial (default 2);
 //               value -1 selects the round-1 scalar arithmetic (A/B measurements), whose polynomial share is key 1
 //   key 1  fwd, scalar arithmetic only: every value-th exponential on the polynomial, value in {0, 4}
-//   key 3  bwd: value in 0..4 of every 8 score pairs on the polynomial (default 0)
+//   key 3  bwd: value in 0..4 of every 8 score pairs on the polynomial (default 1)
 extern "C" int gd_attn_sm100_config(int key, int value) {
     switch (key) {
         case 0: if (value < -1 || value > 4) break; g_np = value; return GD_OK;
