@@ -248,7 +248,15 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
 
     def _ensure_device_state(self, device):
         if self._log_accum is None or self._log_accum.device != device:
-            self._log_accum = torch.zeros(2, 6, device=device, dtype=torch.float32)
+            # with a per-model arena the accumulator (and the removal weight below) sit at a fixed address, like the caches: a recorded
+            # optimisation pass of an earlier edit writes into the buffers the current controller reads
+            if self._arena is not None:
+                buf = self._arena.get("log_accum")
+                if buf is None or buf.device != device:
+                    buf = self._arena["log_accum"] = torch.zeros(2, 6, device=device, dtype=torch.float32)
+                self._log_accum = buf
+            else:
+                self._log_accum = torch.zeros(2, 6, device=device, dtype=torch.float32)
             n = self.loss_log_dict["num_layers"] if self.loss_log_dict else 0
             self.initialize_loss_log_dict()
             self.loss_log_dict["num_layers"] = n
@@ -297,7 +305,13 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         CUDA graph captured for one optimisation pass stays valid after the schedule has moved them.  Two 4-byte fills; no host sync."""
         w = (float(self.loss_weight_dict["self"].get("removal", 0.0)), float(self.loss_weight_dict["cross"].get("removal", 0.0)))
         if self._w_rem_dev is None or self._w_rem_dev.device != device:
-            self._w_rem_dev = torch.zeros(2, device=device, dtype=torch.float32)
+            if self._arena is not None:
+                buf = self._arena.get("w_rem_dev")
+                if buf is None or buf.device != device:
+                    buf = self._arena["w_rem_dev"] = torch.zeros(2, device=device, dtype=torch.float32)
+                self._w_rem_dev = buf
+            else:
+                self._w_rem_dev = torch.zeros(2, device=device, dtype=torch.float32)
             self._w_rem_host = None
         if self._w_rem_host != w:
             self._w_rem_dev[0].fill_(w[0])

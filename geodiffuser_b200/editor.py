@@ -232,6 +232,8 @@ def make_controller(model, staged, transform_in, edit_type, hp, num_ddim_steps=5
     # (edits on one model are sequential: one live controller per model)
     controller._arena = model.__dict__.setdefault("_arenas", {}).setdefault(cls.__name__, {})
     controller._unet_graphs = model.__dict__.setdefault("_edit_graphs", {}).setdefault(cls.__name__, {})
+    controller._grad_graphs = model.__dict__.setdefault("_grad_graph_store", {}).setdefault(cls.__name__, {})
+    controller._grad_graphs_shared = True    # graphs.grad_pass: keyed on the edit's fingerprint (inpaint-row counts, mask sums), reused across edits
     controller.image_mask = staged["obj_mask"][None].tile(2, 1, 1)
     controller.amodal_mask = geometry.torch_erode(mesh[None, None])  # editor.py:633
     if hp.get("loss_weights_dict") is not None:

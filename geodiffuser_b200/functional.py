@@ -67,12 +67,13 @@ class ResolutionCache:
         self.one_minus_m_edit = keep("one_minus_m_edit", 1.0 - self.m_edit)
         self.m_inp_plus_bg = keep("m_inp_plus_bg", self.m_inp + self.m_bg)
         rows = torch.nonzero(self.m_inp > 0.5).reshape(-1).to(torch.int32)
-        self.rows = rows.contiguous()
         self.M = int(rows.numel())
         rowmap = torch.full((self.N,), -1, device=dev, dtype=torch.int32)
         if self.M:
             rowmap[rows.long()] = torch.arange(self.M, device=dev, dtype=torch.int32)
-        self.rowmap = rowmap
+        # (in the arena as well: an optimisation-pass graph recorded for one edit then serves every later edit with the same inpaint-row
+        #  counts and mask sums -- graphs.grad_pass keys on them)
+        self.rows, self.rowmap = keep("rows", rows), keep("rowmap", rowmap)
         self.sum_bg, self.sum_edit, self.sum_inp = float(self.m_bg.sum()), float(self.m_edit.sum()), float(self.m_inp.sum())
         self.idx = self.dist2 = None
         if coords_S is not None:
@@ -81,9 +82,15 @@ class ResolutionCache:
         self.knn_idx = self.knn_val = self.knn_w = None
         self.sum_w_am = 0.0
         if need_amodal:
-            self.knn_idx = torch.empty(self.N, 4, device=dev, dtype=torch.int32)
-            self.knn_val = torch.empty(self.N, 4, device=dev, dtype=torch.float32)
-            self.knn_w = torch.empty(self.N, device=dev, dtype=torch.float32)
+            def buf(name, shape, dtype):
+                b = arena.get((S, name)) if arena is not None else None
+                if b is None or b.shape != torch.Size(shape) or b.device != dev:
+                    b = torch.empty(*shape, device=dev, dtype=dtype)
+                    if arena is not None:
+                        arena[(S, name)] = b
+                        arena["generation"] = arena.get("generation", 0) + 1
+                return b
+            self.knn_idx, self.knn_val, self.knn_w = buf("knn_idx", (self.N, 4), torch.int32), buf("knn_val", (self.N, 4), torch.float32), buf("knn_w", (self.N,), torch.float32)
             call("gd_amodal_knn", ptr(self.m_edit), S, ptr(self.knn_idx), ptr(self.knn_val), ptr(self.knn_w), stream())
             self.sum_w_am = float((self.knn_w * self.m_am).sum())
 

@@ -25,6 +25,7 @@ _CAPTURE_LOCK = threading.RLock()   # one capture at a time per process: the gar
                                     # cudaErrorStreamCaptureInvalidated.  Replays never take it.
 ENABLED = True      # product default; tests compare against the eager path by switching it off
 GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as well
+MAX_SHARED_GRAD_GRAPHS = 6           # optimisation-pass graphs kept per (model, controller kind) for reuse by later edits with the same fingerprint
 CAPTURE_ERROR_MODE = "thread_local"   # cudaStreamCaptureMode of the hand-driven captures: CUDA calls that OTHER threads make meanwhile (another
                                       # edit lane's allocations, event queries) stay legal
 
@@ -259,8 +260,23 @@ def grad_pass(model, controller, latents, context, t):
     store = controller.__dict__.setdefault("_grad_graphs", {})
     lw = controller.loss_weight_dict
     weights = tuple(sorted((a, k, float(v)) for a in ("self", "cross") for k, v in lw[a].items() if k != "removal"))
-    key = (controller_key(controller), weights, tuple(latents.shape), tuple(context.shape), id(model.unet))
+    # What a recorded pass bakes in besides pointers: per resolution the inpaint-row count M (buffer shapes) and the mask sums (the loss
+    # normalisers are kernel arguments).  Everything else it reads -- masks, row lists, splat index, amodal tables, base stores, log accumulator,
+    # removal weight -- sits in the per-model arena at fixed addresses and is refreshed in place by the next edit, so with an arena the graph
+    # of one edit serves every later edit with the same fingerprint (editor.make_controller keeps the store on the model); without one the
+    # store is the controller's own and dies with it.
+    arena = controller.__dict__.get("_arena")
+    shared = arena is not None and controller.__dict__.get("_grad_graphs_shared", False)
+    if shared:
+        _prebuild_caches(model, controller, latents)
+    finger = tuple(sorted((S, c.M, c.sum_bg, c.sum_edit, c.sum_inp, c.sum_w_am) for S, c in getattr(controller, "_res_cache", {}).items())) if shared else id(controller)
+    key = (controller_key(controller), weights, tuple(latents.shape), tuple(context.shape), id(model.unet), finger,
+           arena.get("generation", 0) if arena is not None else -1)
     g = store.get(key)
+    if g is not None and g != "warm" and shared:
+        store[key] = store.pop(key)             # most recently used last
+    while shared and len(store) > MAX_SHARED_GRAD_GRAPHS:
+        store.pop(next(iter(store)))            # each holds the activations of one forward + backward in the graph pool
     # what a backward capture needs warmed up (cuBLAS / cuDNN handles and workspaces, cudnn.benchmark choices, the side stream's allocator
     # cache) belongs to the process and the model, not to the edit: once one eager pass of this kind and shape has run on this model, the next
     # edit captures its first optimisation pass directly -- after building its per-resolution caches, which synchronise and so cannot be
