@@ -272,7 +272,8 @@ def run_edit(model, staged, transform_in, edit_type="geometry_editor", num_ddim_
         uncond_embeddings=uncond, text_embeddings=text, transform_coordinates=transform_coordinates, mask_obj=staged["obj_mask"],
         optimize_steps=hp["optimize_steps"], latent_replace=hp["latent_replace"], lr=hp["lr"], optimize_embeddings=hp["optimize_embeddings"],
         optimize_latents=hp["optimize_latents"], ddim_latents=ddim_latents, edit_type=edit_type, skip_optim_steps=hp["skip_optim_steps"],
-        removal_loss_value_in=hp.get("removal_loss_value_in", -1.5))
+        removal_loss_value_in=hp.get("removal_loss_value_in", -1.5), fast_start_steps=hp.get("fast_start_steps", 0.0),
+        num_first_optim_steps=hp.get("num_first_optim_steps", 5))
     model.unet.set_attn_processor(VanillaAttentionProcessor())  # editor.py:698
     if return_log:
         return latents, log

@@ -92,12 +92,18 @@ def main():
     torch.set_num_threads(os.cpu_count())
     R = load_reference()
     only = sys.argv[sys.argv.index("--only") + 1] if "--only" in sys.argv else None     # e.g. --only remove
-    if "--full-only" not in sys.argv:
+    if "--full-only" not in sys.argv and "--full50" not in sys.argv:
         for kind in ("translate2d", "rotate3d", "remove"):
             if only in (None, kind):
                 run_case(f"{kind}_tiny", kind, True, 10, True, R)
     if "--full" in sys.argv or "--full-only" in sys.argv:
         run_case("translate2d_full5", "translate2d", False, 5, False, R, inversion=False)
+    if "--full50" in sys.argv:
+        # BASELINE.json configs[1] and configs[2] at full size: SD-1.5 topology, 50-step DDIM inversion + 50-step edit (3-D rotation with latent
+        # optimisation; object removal).  ~15 minutes of CPU time each on 8 cores.
+        kinds = [sys.argv[sys.argv.index("--full50") + 1]] if len(sys.argv) > sys.argv.index("--full50") + 1 else ["rotate3d", "remove"]
+        for kind in kinds:
+            run_case(f"{kind}_full50", kind, False, 50, False, R, inversion=True)
 
 
 if __name__ == "__main__":

@@ -407,3 +407,22 @@ def test_optimisation_graph_is_reused_by_the_next_edit_with_the_same_fingerprint
     p = psnr(a[1].numpy(), b[1].numpy())
     print(f"edit replaying another edit's optimisation graph vs its own: PSNR {p:.1f} dB")
     assert torch.equal(a[0], b[0]) and p >= 60.0
+
+
+def test_fast_start_steps_follow_the_reference_control_flow(tiny_model, monkeypatch):
+    """editor.py:354-355, 375-377, 382-399: on a fast-start step (i < fast_start_steps * n) only the diffusion step is skipped -- the reference
+    latent is still replaced by the inversion trajectory and the edit latent is still set to reference * (1 - m) + m * warp(reference)
+    (`fast` branch of the latent warp); the first optimisation step after the fast start runs num_first_optim_steps passes."""
+    from geodiffuser_b200 import editor, graphs
+
+    calls, passes = [], []
+    real_warp, real_grad = editor._latent_warp_replace, graphs.grad_pass
+    monkeypatch.setattr(editor, "_latent_warp_replace", lambda c, l, tc, fast=False: (calls.append(bool(fast)), real_warp(c, l, tc, fast=fast))[1])
+    monkeypatch.setattr(graphs, "grad_pass", lambda *a, **k: (passes.append(a[1].cur_step), real_grad(*a, **k))[1])
+    lat, log = editor.perform_synthetic_edit(tiny_model, "translate2d", num_ddim_steps=10, return_log=True, fast_start_steps=0.2, num_first_optim_steps=3)
+    assert torch.isfinite(lat).all()
+    assert calls[:2] == [True, True] and not any(calls[2:])          # steps 0, 1: fast warp; later only the latent_replace window (i < 1: none)
+    assert 0 not in log and 1 not in log and 2 in log                 # no optimisation on the fast-start steps; the first one is step 2 ...
+    assert passes.count(passes[0]) == 3                               # ... with num_first_optim_steps passes, the later ones with one
+    base = editor.perform_synthetic_edit(tiny_model, "translate2d", num_ddim_steps=10)
+    assert float((lat[1] - base[1]).abs().max()) > 0                  # a different trajectory than without the fast start
