@@ -149,3 +149,41 @@ def test_projection_view_and_slab_strides():
     assert tuple(lay.new_batch(q, 2, N).shape) == (2, N, H * d) and tuple(lay_h.new_batch(qh, 2, N).shape) == (2 * H, N, d)
     st = lay.strides(out=lay.kv)
     assert list(st) == [H * d, d, H * d, d, H * d, d]
+
+
+def test_algorithmic_flop_formulas_match_survey_8d():
+    """forward 3 x 4 H N^2 d = 64.4 GF, backward 6 H N^2 d = 32.2 GF at the 64^2 level; correlation 2 H M N^2 = 110 GF at M = 410"""
+    from geodiffuser_b200 import _lib
+
+    assert abs(_lib.algorithmic_flops("gd_attn_fwd_sm100", (3, 8, 4096, 4096, 40)) / 1e9 - 64.4) < 0.05
+    assert abs(_lib.algorithmic_flops("gd_attn_bwd_sm100", (8, 4096, 4096, 40)) / 1e9 - 32.2) < 0.05
+    assert abs(_lib.algorithmic_flops("gd_removal_corr_sm100", (8, 410, 4096, 4096)) / 1e9 - 110.0) < 0.1
+    assert _lib.algorithmic_flops("gd_attn_probs", (8, 410, 4096, 40)) == 0.0           # implementation work, not in the survey's count
+    assert _lib.algorithmic_flops("gd_attn_fwd_generic", None) == 0.0
+
+
+def test_launch_counters_are_per_thread_and_sum_up():
+    """runner.EditWorkers drives one GPU from several host threads: each books its launches on its own counters (a CUDA-graph capture subtracts
+    what it recorded from the capturing thread only); the module attributes read the totals; count_into books on another thread's counters."""
+    import threading
+    from geodiffuser_b200 import _lib
+
+    base_l, base_f = _lib.LAUNCHES, _lib.FLOPS
+    mine = _lib.counters()
+    seen = {}
+
+    def lane(n):
+        c = _lib.counters()
+        c.launches += n
+        c.flops += 10.0 * n
+        seen[n] = c
+        with _lib.count_into(mine):
+            _lib.counters().launches += 100 * n
+
+    ts = [threading.Thread(target=lane, args=(n,)) for n in (1, 2)]
+    l0 = mine.launches
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert seen[1] is not seen[2] and seen[1] is not mine
+    assert (seen[1].launches, seen[2].launches) == (1, 2) and mine.launches - l0 == 300
+    assert _lib.LAUNCHES - base_l == 303 and _lib.FLOPS - base_f == 30.0
