@@ -426,3 +426,33 @@ def test_fast_start_steps_follow_the_reference_control_flow(tiny_model, monkeypa
     assert passes.count(passes[0]) == 3                               # ... with num_first_optim_steps passes, the later ones with one
     base = editor.perform_synthetic_edit(tiny_model, "translate2d", num_ddim_steps=10)
     assert float((lat[1] - base[1]).abs().max()) > 0                  # a different trajectory than without the fast start
+
+
+# measured on B200 (edited-latent PSNR vs the fp32 CPU oracle loop after the full 50-step edit, full SD-1.5 topology); see the test below
+FULL50_GATE = {torch.float32: {"rotate3d": 40.0, "remove": 40.0}, torch.bfloat16: {"rotate3d": 40.0, "remove": 40.0}}
+
+
+@pytest.mark.timeout(900)
+@pytest.mark.parametrize("body_dtype", [torch.float32, torch.bfloat16], indirect=True, ids=["fp32body", "bf16body"])
+@pytest.mark.parametrize("kind", ["rotate3d", "remove"])
+def test_config1_config2_full_sd15_50_steps_vs_oracle_golden(full_model, kind, body_dtype):
+    """BASELINE.json configs[1] (50-step DDIM inversion + 3-D rotation edit with latent optimisation -- the configuration bench.py times) and
+    configs[2] (object removal, 50 steps) at FULL size against the CPU oracle loop's golden (oracle/make_golden_loop.py --full50: ~20 minutes
+    of CPU time each).  Gate (BASELINE.json): final edited latent PSNR >= 40 dB; first-pass loss within 2e-2."""
+    from geodiffuser_b200 import editor
+
+    path = os.path.join(GOLDEN, f"loop_{kind}_full50.npz")
+    if not os.path.exists(path):
+        pytest.skip("golden not generated")
+    z = np.load(path)
+    assert int(z["meta"][0]) == 0 and int(z["meta"][1]) == 50 and int(z["meta"][2]) == 1
+    lat, log = editor.perform_synthetic_edit(full_model, kind, num_ddim_steps=50, return_log=True)
+    lat = lat.float().cpu().numpy()
+    assert np.isfinite(lat).all()
+    assert abs(log[0]["loss"] - float(z["log0_loss"])) <= 2e-2 * abs(float(z["log0_loss"])), (log[0]["loss"], float(z["log0_loss"]))
+    p_ref, p_edit = psnr(lat[0], z["latents"][0]), psnr(lat[1], z["latents"][1])
+    last = max(k for k in log)
+    print(f"configs[{1 if kind == 'rotate3d' else 2}] full SD-1.5, 50 steps [{body_dtype}]: PSNR reference-branch latent {p_ref:.1f} dB, edited latent {p_edit:.1f} dB; "
+          f"loss step 0 {log[0]['loss']:.4f} / {float(z['log0_loss']):.4f}, step {last} {log[last]['loss']:.4f} / {float(z[f'log{last}_loss']):.4f}")
+    assert p_ref >= 40.0
+    assert p_edit >= FULL50_GATE[body_dtype][kind]
