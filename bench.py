@@ -30,7 +30,7 @@ N_OPT, N_CFG, N_INV = 17, 50, 50   # UNet passes per edit with the perform_exp h
 
 def bench_config(n):
     """the same dict in both arms (the driver compares them)"""
-    return {"workload": WORKLOAD, "parallelism": f"request-level dp{n} (independent edits, no collective; 3 edit lanes per GPU in the GPU arm)",
+    return {"workload": WORKLOAD, "parallelism": f"request-level dp{n} (independent edits, no collective; 4 edit lanes per GPU in the GPU arm)",
             "l2": "no flush needed: every UNet pass streams 1.7 GB of weights + activations (> 126 MB L2) between repeats"}
 
 
@@ -294,29 +294,6 @@ def run_ours(args):
         roofs = kernel_rooflines(dev, M64, M32, peaks)
         if not roofs:
             raise SystemExit("bench.py: the roofline leg produced nothing")
-        # ... and IN the loop: one more edit with the optimisation pass run eagerly (graphs.GRAD_ENABLED = False), CUDA events around every launch
-        # of the forward / backward / correlation kernels inside it (17 passes x 5 layers at the 64^2 level): the kernel as it runs between the
-        # body's kernels, against the SUSTAINED bf16 peak
-        from geodiffuser_b200 import graphs
-        graphs.GRAD_ENABLED = False
-        try:
-            _lib.profile_begin(["gd_attn_fwd_sm100", "gd_attn_bwd_sm100", "gd_removal_corr_sm100"])
-            editor.run_edit(model, staged, req["transform_in"], req["edit_type"])
-            torch.cuda.synchronize(dev)
-            prof = _lib.profile_end()
-        finally:
-            graphs.GRAD_ENABLED = True
-        pk_s = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
-        in_loop = {}
-        for name, sel, label in (("gd_attn_fwd_sm100", lambda t: t[2] == 4096 and t[0] == 3, "attn_fwd_sm100_kernel<40> G=3 H=8 N=4096"),
-                                 ("gd_attn_bwd_sm100", lambda t: t[1] == 4096, f"attn_bwd64_sm100_kernel<40> H=8 N=4096 M={M64}"),
-                                 ("gd_removal_corr_sm100", lambda t: t[2] == 4096, f"removal_corr_sm100_kernel<40> H=8 N=4096 M={M64}")):
-            ev = [(ms, t) for ms, t in prof.get(name, []) if t is not None and sel(t)]
-            if ev:
-                fl = sum(_lib.algorithmic_flops(name, t) for _, t in ev)
-                ms = sum(m for m, _ in ev)
-                in_loop[label] = {"achieved": fl / (ms * 1e-3) / 1e12, "unit": "TFLOP/s", "peak": pk_s, "frac": fl / (ms * 1e-3) / 1e12 / pk_s,
-                                  "launches": len(ev), "avg_launch_ms": ms / len(ev)}
 
     if rank == 0:
         value = world * args.steps / (ms_value / 1e3)
@@ -324,7 +301,6 @@ def run_ours(args):
         roof = dict(roofs[0])
         roof["peak_source"] = peak_src + ": burst bf16 (kernel timed alone, back to back); frac_sustained = against the sustained figure"
         roof["other_kernels"] = roofs[1:]
-        roof["in_loop"] = in_loop      # same kernels timed inside an edit (eager optimisation passes), against the sustained peak
         pk_s = peaks.get("bf16_tflops_sustained", peaks["bf16_tflops"])
         # the whole edit against the attention roofline (north_star): algorithmic attention-path FLOP of one edit / step time / peak
         roof["edit_level"] = {"attention_path_flops_per_edit": flops_per_edit,
@@ -398,7 +374,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="config1", choices=["config1", "mixed64"],
                     help="config1 = BASELINE configs[1] (the metric's configuration); mixed64 = configs[4], the 64-edit mixed sweep")
-    ap.add_argument("--lanes", type=int, default=3, help="independent edits in flight per GPU (1 = one edit at a time)")
+    ap.add_argument("--lanes", type=int, default=4, help="independent edits in flight per GPU (1 = one edit at a time)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -246,13 +246,19 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
     def initialize_default_loss_weights(self):
         self.loss_weight_dict = self.default_loss_weights  # aliasing is the reference's behaviour
 
+    @staticmethod
+    def _on(t, device):
+        """is tensor `t` on `device`?  (`device` may come without an index -- torch.device("cuda") -- which never compares equal to a tensor's)"""
+        device = torch.device(device)
+        return t is not None and t.device.type == device.type and (device.index is None or t.device.index == device.index)
+
     def _ensure_device_state(self, device):
-        if self._log_accum is None or self._log_accum.device != device:
+        if not self._on(self._log_accum, device):
             # with a per-model arena the accumulator (and the removal weight below) sit at a fixed address, like the caches: a recorded
             # optimisation pass of an earlier edit writes into the buffers the current controller reads
             if self._arena is not None:
                 buf = self._arena.get("log_accum")
-                if buf is None or buf.device != device:
+                if not self._on(buf, device):
                     buf = self._arena["log_accum"] = torch.zeros(2, 6, device=device, dtype=torch.float32)
                 self._log_accum = buf
             else:
@@ -304,10 +310,10 @@ class _GeometryControllerBase(AttentionStore, abc.ABC):
         """Mirrors the removal-loss weights (the only ones the adaptive schedule changes, optimization.py:7-105) into device memory, so that a
         CUDA graph captured for one optimisation pass stays valid after the schedule has moved them.  Two 4-byte fills; no host sync."""
         w = (float(self.loss_weight_dict["self"].get("removal", 0.0)), float(self.loss_weight_dict["cross"].get("removal", 0.0)))
-        if self._w_rem_dev is None or self._w_rem_dev.device != device:
+        if not self._on(self._w_rem_dev, device):
             if self._arena is not None:
                 buf = self._arena.get("w_rem_dev")
-                if buf is None or buf.device != device:
+                if not self._on(buf, device):
                     buf = self._arena["w_rem_dev"] = torch.zeros(2, device=device, dtype=torch.float32)
                 self._w_rem_dev = buf
             else:

@@ -25,6 +25,7 @@ _CAPTURE_LOCK = threading.RLock()   # one capture at a time per process: the gar
                                     # cudaErrorStreamCaptureInvalidated.  Replays never take it.
 ENABLED = True      # product default; tests compare against the eager path by switching it off
 GRAD_ENABLED = True  # the optimisation pass (forward + backward) as a graph as well
+SHARE_GRAD_GRAPHS = True             # reuse an edit's recorded optimisation pass for later edits with the same fingerprint (False: one capture per edit)
 MAX_SHARED_GRAD_GRAPHS = 6           # optimisation-pass graphs kept per (model, controller kind) for reuse by later edits with the same fingerprint
 CAPTURE_ERROR_MODE = "thread_local"   # cudaStreamCaptureMode of the hand-driven captures: CUDA calls that OTHER threads make meanwhile (another
                                       # edit lane's allocations, event queries) stay legal
@@ -266,7 +267,7 @@ def grad_pass(model, controller, latents, context, t):
     # of one edit serves every later edit with the same fingerprint (editor.make_controller keeps the store on the model); without one the
     # store is the controller's own and dies with it.
     arena = controller.__dict__.get("_arena")
-    shared = arena is not None and controller.__dict__.get("_grad_graphs_shared", False)
+    shared = SHARE_GRAD_GRAPHS and arena is not None and controller.__dict__.get("_grad_graphs_shared", False)
     if shared:
         _prebuild_caches(model, controller, latents)
     finger = tuple(sorted((S, c.M, c.sum_bg, c.sum_edit, c.sum_inp, c.sum_w_am) for S, c in getattr(controller, "_res_cache", {}).items())) if shared else id(controller)
