@@ -10,7 +10,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgeodiffuser_b200.so")
+LIB_PATH = os.environ.get("GD_LIB_PATH") or os.path.join(_HERE, "libgeodiffuser_b200.so")   # (GD_LIB_PATH: A/B builds of kernel variants)
 
 P, I, F, L = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_long
 

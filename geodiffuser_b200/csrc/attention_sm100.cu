@@ -37,44 +37,75 @@ struct Sm100Params {
     int os_bf16;
     int H, N, d;
     float scale2;  // scale * log2(e)
+#ifdef GD_TRACE
+    long long* trace;   // scripts/fwd_trace.cu: clock64 stamps of one CTA's warps, [role][step][8]
+    int trace_x;
+#endif
 };
+#ifdef GD_TRACE
+#define GD_TR(role, j, slot) do { if (p.trace && blockIdx.x == p.trace_x && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x & 31) == 0) \
+    p.trace[((role) * 256 + (j)) * 8 + (slot)] = clock64(); } while (0)
+#else
+#define GD_TR(role, j, slot) do { } while (0)
+#endif
 
 // D = head_dim (40 or 80).  KB = number of 64-wide (128-byte) column blocks per operand row; KSTEPS = ceil(D/16); DV = O columns.
-// NP >= 0 (the product path): packed fp32x2 softmax arithmetic, NP of every 8 score pairs on the FMA-pipe polynomial, the rest on the MUFU.
-// NP < 0 (round-1 arithmetic, kept for A/B measurements): scalar ops, POLY = every POLY-th exponential on the polynomial (0 = none).
-template <int D, int POLY, int NP>
-__global__ void __launch_bounds__(SM100_THREADS, (D <= 64) ? 2 : 1)
+// BNK = keys per step (128 or 64).  Packed fp32x2 softmax arithmetic, NP of every 8 score pairs on the FMA-pipe polynomial, the rest on the MUFU.
+//
+// BNK = 128: TMEM [0,128) S | [128,192) P | [192,192+DV) O in one allocation of 256 (head_dim 40: two CTAs per SM) or 512 columns (head_dim 80).
+// BNK =  64: S 64 + P 32 + O DV columns.  head_dim 40: 144 columns, taken as TWO allocations (128: S | O, and 32: P) so that THREE CTAs fit the
+//            512 columns of an SM (allocations are powers of two; 3 x 160 = 480) -- twelve softmax warps per SM instead of eight, three per
+//            scheduler: the softmax chain of a tile (wait, tcgen05.ld, row max, exponentials, tcgen05.st, handshake) keeps a warp off the MUFU
+//            for more than half of its time, and a third resident chain is what fills that pipe.  A CTA that blocks in tcgen05.alloc waits for
+//            a CTA that never waits for it, so the split allocation cannot deadlock; shared memory (64 KB per CTA) keeps a fourth CTA out.
+//            head_dim 80: 176 columns -> one allocation of 256, two CTAs per SM (one at BNK = 128).
+template <int D, int BNK> struct FwdCfg {
+    static constexpr int KSTEPS = (D + 15) / 16;
+    static constexpr int DV = KSTEPS * 16;
+    static constexpr bool SPLIT_ALLOC = (BNK == 64 && DV <= 64);
+    static constexpr int CTAS = (BNK == 64) ? (DV <= 64 ? 3 : 2) : (192 + DV <= 256 ? 2 : 1);
+    static constexpr int NSTAGE = SPLIT_ALLOC ? 3 : 2;
+    static constexpr int TMEM_COLS = SPLIT_ALLOC ? 128 : (BNK == 64 ? 256 : (192 + DV <= 256 ? 256 : 512));
+    static constexpr uint32_t COL_S = 0;
+    static constexpr uint32_t COL_O = SPLIT_ALLOC ? 64 : (BNK == 64 ? 96 : 192);
+    static constexpr uint32_t COL_P = SPLIT_ALLOC ? 0 : (BNK == 64 ? 64 : 128);      // SPLIT_ALLOC: relative to the second allocation
+    static constexpr int KB = (D + 63) / 64;
+    static constexpr size_t SMEM = (size_t)KB * 128 * 128 + (size_t)NSTAGE * 2 * KB * BNK * 128 + 256 + 1024;
+};
+
+template <int D, int BNK, int NP>
+__global__ void __launch_bounds__(SM100_THREADS, (FwdCfg<D, BNK>::CTAS))
 attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params p) {
-    constexpr int KB = (D + 63) / 64;
-    constexpr int KSTEPS = (D + 15) / 16;
-    constexpr int DV = KSTEPS * 16;                 // 48 / 80: UMMA N (multiple of 16 at M = 128)
-    constexpr int TILE_BYTES = 128 * 128;           // one [128 rows][64 bf16] swizzled block
-    constexpr int OP_BYTES = KB * TILE_BYTES;       // one operand tile (Q, K or V)
-    constexpr int TMEM_COLS = (192 + DV <= 256) ? 256 : 512;
-    constexpr uint32_t COL_S = 0, COL_P = 128, COL_O = 192;
-    constexpr int NSTAGE = 2;
+    typedef FwdCfg<D, BNK> C;
+    constexpr int KB = C::KB;
+    constexpr int KSTEPS = C::KSTEPS;
+    constexpr int DV = C::DV;                       // 48 / 80: UMMA N (multiple of 16 at M = 128)
+    constexpr int QTILE_BYTES = 128 * 128;          // one [128 rows][64 bf16] swizzled block of Q
+    constexpr int KTILE_BYTES = BNK * 128;          // one [BNK rows][64 bf16] swizzled block of K / V
+    constexpr int Q_BYTES = KB * QTILE_BYTES, K_BYTES = KB * KTILE_BYTES;
+    constexpr int NSTAGE = C::NSTAGE;
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     unsigned char* sQ = smem;
-    unsigned char* sK = sQ + OP_BYTES;
-    unsigned char* sV = sK + NSTAGE * OP_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTAGE * OP_BYTES);
+    unsigned char* sK = sQ + Q_BYTES;
+    unsigned char* sV = sK + NSTAGE * K_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NSTAGE * K_BYTES);
     uint64_t* q_full = bars + 0;
-    uint64_t* k_full = bars + 1;    // [2]
-    uint64_t* k_empty = bars + 3;   // [2]
-    uint64_t* v_full = bars + 5;    // [2]
-    uint64_t* v_empty = bars + 7;   // [2]
-    uint64_t* s_full = bars + 9;
-    uint64_t* s_free = bars + 10;
-    uint64_t* p_full = bars + 11;
-    uint64_t* pv_done = bars + 12;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* s_full = bars + 1;
+    uint64_t* s_free = bars + 2;
+    uint64_t* p_full = bars + 3;
+    uint64_t* pv_done = bars + 4;
+    uint64_t* k_full = bars + 5;                  // [NSTAGE]
+    uint64_t* k_empty = k_full + NSTAGE;
+    uint64_t* v_full = k_empty + NSTAGE;
+    uint64_t* v_empty = v_full + NSTAGE;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + NSTAGE);   // [2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
     const int N = p.N;
-    const int nT = N / BN;
+    const int nT = N / BNK;
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
@@ -83,70 +114,85 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 5) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(C::TMEM_COLS) : "memory");
+        if constexpr (C::SPLIT_ALLOC)
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot + 1)), "r"(32) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 4 && lane == 0) { tma_prefetch_desc(&maps.q[g]); tma_prefetch_desc(&maps.k[g]); tma_prefetch_desc(&maps.v[g]); }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_slot[0], 0);
+    const uint32_t tS = tmem + C::COL_S, tO = tmem + C::COL_O, tP = (C::SPLIT_ALLOC ? __shfl_sync(0xffffffffu, tmem_slot[1], 0) : tmem) + C::COL_P;
 
     if (warp == 4) {
-        // ================= TMA producer (runs up to two stages ahead: its waits are not latency critical) =================
+        // ================= TMA producer (runs up to NSTAGE stages ahead: its waits are not latency critical) =================
         if (lane == 0) {
-            mbar_expect_tx(q_full, OP_BYTES);
+            mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
-            for (int b = 0; b < KB; ++b) tma_load_3d(sQ + b * TILE_BYTES, &maps.q[g], q_full, b * 64, q0, h);
+            for (int b = 0; b < KB; ++b) tma_load_3d(sQ + b * QTILE_BYTES, &maps.q[g], q_full, b * 64, q0, h);
             for (int j = 0; j < nT; ++j) {
-                const int s = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
+                const int s = j % NSTAGE;
+                const uint32_t ph = (j / NSTAGE) & 1;
                 mbar_wait_relaxed(k_empty + s, ph ^ 1);
-                mbar_expect_tx(k_full + s, OP_BYTES);
+                GD_TR(5, j, 0);
+                mbar_expect_tx(k_full + s, K_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_3d(sK + s * OP_BYTES + b * TILE_BYTES, &maps.k[g], k_full + s, b * 64, j * BN, h);
+                for (int b = 0; b < KB; ++b) tma_load_3d(sK + s * K_BYTES + b * KTILE_BYTES, &maps.k[g], k_full + s, b * 64, j * BNK, h);
                 mbar_wait_relaxed(v_empty + s, ph ^ 1);
-                mbar_expect_tx(v_full + s, OP_BYTES);
+                GD_TR(5, j, 1);
+                mbar_expect_tx(v_full + s, K_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * OP_BYTES + b * TILE_BYTES, &maps.v[g], v_full + s, b * 64, j * BN, h);
+                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * K_BYTES + b * KTILE_BYTES, &maps.v[g], v_full + s, b * 64, j * BNK, h);
             }
         }
     } else if (warp == 5) {
         // ================= MMA issuer =================
+#ifdef GD_MMA_LANE0
         if (lane == 0) {
-            constexpr uint32_t IDESC_QK = make_idesc(BM, BN, 0, 0);
+#else
+        {   // all 32 lanes walk the loop; one elected lane issues (umma_*_w, tc_commit_w)
+#endif
+            constexpr uint32_t IDESC_QK = make_idesc(BM, BNK, 0, 0);
             constexpr uint32_t IDESC_PV = make_idesc(BM, DV, 0, 1);
             const uint32_t aQ = smem_addr(sQ);
             auto issue_qk = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(k_full + s, (j >> 1) & 1);
-                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                const int s = j % NSTAGE;
+                GD_TR(4, j, 0);
+                mbar_wait_mma(k_full + s, (j / NSTAGE) & 1);
+                GD_TR(4, j, 1);
+                if (j > 0) mbar_wait_mma(s_free, (j - 1) & 1);
+                GD_TR(4, j, 2);
                 tc_fence_after();
-                const uint32_t aK = smem_addr(sK + s * OP_BYTES);
+                const uint32_t aK = smem_addr(sK + s * K_BYTES);
 #pragma unroll
-                for (int ks = 0; ks < KSTEPS; ++ks) {
-                    const uint32_t off = (ks >> 2) * TILE_BYTES + (ks & 3) * 32;   // 64-wide block, then 32 B per 16 elements
-                    umma_ss(tmem + COL_S, make_desc(aQ + off, 16, 1024), make_desc(aK + off, 16, 1024), IDESC_QK, ks > 0);
-                }
-                tc_commit(s_full);        // S(j) complete -> softmax
-                tc_commit(k_empty + s);   // K stage reusable
+                for (int ks = 0; ks < KSTEPS; ++ks)     // 64-wide block, then 32 B per 16 elements
+                    umma_ss_w(tS, make_desc(aQ + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
+                            make_desc(aK + (ks >> 2) * KTILE_BYTES + (ks & 3) * 32, 16, 1024), IDESC_QK, ks > 0);
+                tc_commit_w(s_full);        // S(j) complete -> softmax
+                tc_commit_w(k_empty + s);   // K stage reusable
             };
-            mbar_wait(q_full, 0);
+            mbar_wait_mma(q_full, 0);
             issue_qk(0);
             for (int j = 0; j < nT; ++j) {
                 if (j + 1 < nT) issue_qk(j + 1);
-                const int s = j & 1;
-                mbar_wait(v_full + s, (j >> 1) & 1);
-                mbar_wait(p_full, j & 1);
+                const int s = j % NSTAGE;
+                GD_TR(4, j, 3);
+                mbar_wait_mma(v_full + s, (j / NSTAGE) & 1);
+                GD_TR(4, j, 4);
+                mbar_wait_mma(p_full, j & 1);
+                GD_TR(4, j, 5);
                 tc_fence_after();
-                const uint32_t aV = smem_addr(sV + s * OP_BYTES);
+                const uint32_t aV = smem_addr(sV + s * K_BYTES);
 #pragma unroll
-                for (int kk = 0; kk < BN / 16; ++kk) {
+                for (int kk = 0; kk < BNK / 16; ++kk) {
                     // V tile rows = keys (the MMA K dimension), MN-major: 16 keys = 16 rows x 128 B; LBO = next 64-wide column block
-                    umma_ts(tmem + COL_O, tmem + COL_P + kk * 8, make_desc(aV + kk * 2048, TILE_BYTES, 1024), IDESC_PV, (j > 0 || kk > 0));
+                    umma_ts_w(tO, tP + kk * 8, make_desc(aV + kk * 2048, KTILE_BYTES, 1024), IDESC_PV, (j > 0 || kk > 0));
                 }
-                tc_commit(pv_done);
-                tc_commit(v_empty + s);
+                tc_commit_w(pv_done);
+                tc_commit_w(v_empty + s);
+                GD_TR(4, j, 6);
             }
         }
     } else {
@@ -155,18 +201,21 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
         const float scale2 = p.scale2;
         float m_run = -INFINITY, l_run = 0.f;
         for (int j = 0; j < nT; ++j) {
+            GD_TR(warp, j, 0);
             mbar_wait(s_full, j & 1);
+            GD_TR(warp, j, 1);
             tc_fence_after();
-            uint32_t sr[BN];
+            uint32_t sr[BNK];
 #pragma unroll
-            for (int c = 0; c < BN / 32; ++c) tmem_ld32(tmem + lane_off + COL_S + c * 32, sr + c * 32);
+            for (int c = 0; c < BNK / 32; ++c) tmem_ld32(tS + lane_off + c * 32, sr + c * 32);
             tmem_wait_ld();
             tc_fence_before();
             if (lane == 0) mbar_arrive(s_free);      // S(j) is in registers: QK^T(j+1) may overwrite it
+            GD_TR(warp, j, 2);
             // row max: four independent FMNMX3 chains
             float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < BN; c += 8) {
+            for (int c = 0; c < BNK; c += 8) {
                 mx0 = max3(mx0, __uint_as_float(sr[c]), __uint_as_float(sr[c + 1]));
                 mx1 = max3(mx1, __uint_as_float(sr[c + 2]), __uint_as_float(sr[c + 3]));
                 mx2 = max3(mx2, __uint_as_float(sr[c + 4]), __uint_as_float(sr[c + 5]));
@@ -178,38 +227,28 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
             const float m_new = grow ? m_cand : m_run;
             const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
             m_run = m_new;
-            float rs0 = 0.f, rs1 = 0.f;
             u64 rsA = 0ull, rsB = 0ull;                           // packed row-sum accumulators (two chains)
             const u64 sc2 = pk2(scale2, scale2), nm2 = pk2(-m_new, -m_new);
 #pragma unroll
-            for (int cc = 0; cc < BN / 32; ++cc) {
+            for (int cc = 0; cc < BNK / 32; ++cc) {
                 uint32_t pk[16];
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const int e = cc * 32 + 2 * c;
                     float p0, p1;
-                    if constexpr (NP >= 0) {
-                        const u64 x2 = fma2(pk2u(sr[e], sr[e + 1]), sc2, nm2);
-                        u64 p2;
-                        if (pair_is_poly<NP>(c)) {
-                            p2 = ex2_poly2(x2);
-                            upk2(p2, p0, p1);
-                        } else {
-                            float x0, x1;
-                            upk2(x2, x0, x1);
-                            p0 = ex2(x0);
-                            p1 = ex2(x1);
-                            p2 = pk2(p0, p1);
-                        }
-                        if (c & 1) rsB = add2(rsB, p2); else rsA = add2(rsA, p2);
+                    const u64 x2 = fma2(pk2u(sr[e], sr[e + 1]), sc2, nm2);
+                    u64 p2;
+                    if (pair_is_poly<NP>(c)) {
+                        p2 = ex2_poly2(x2);
+                        upk2(p2, p0, p1);
                     } else {
-                        const float x0 = fmaf(__uint_as_float(sr[e]), scale2, -m_new);
-                        const float x1 = fmaf(__uint_as_float(sr[e + 1]), scale2, -m_new);
-                        p0 = use_poly<POLY>(e) ? ex2_poly(x0) : ex2(x0);
-                        p1 = use_poly<POLY>(e + 1) ? ex2_poly(x1) : ex2(x1);
-                        rs0 += p0;
-                        rs1 += p1;
+                        float x0, x1;
+                        upk2(x2, x0, x1);
+                        p0 = ex2(x0);
+                        p1 = ex2(x1);
+                        p2 = pk2(p0, p1);
                     }
+                    if (c & 1) rsB = add2(rsB, p2); else rsA = add2(rsA, p2);
                     __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
                     pk[c] = *reinterpret_cast<uint32_t*>(&b2);
                 }
@@ -217,31 +256,32 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
                     // P(j) may overwrite P(j-1), and O may be corrected, only once PV(j-1) has completed.  Waiting here -- one chunk of
                     // exponentials after the row max -- instead of in front of the exponentials keeps the MMA round trip
                     // (p_full -> PV issue -> commit) off the softmax warps' critical path.
+                    GD_TR(warp, j, 3);
                     mbar_wait(pv_done, (j - 1) & 1);
+                    GD_TR(warp, j, 4);
                     tc_fence_after();
                     if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll
                         for (int c = 0; c < DV / 16; ++c) {
                             uint32_t orr[16];
-                            tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
+                            tmem_ld16(tO + lane_off + c * 16, orr);
                             tmem_wait_ld();
 #pragma unroll
                             for (int e = 0; e < 16; ++e) orr[e] = __float_as_uint(__uint_as_float(orr[e]) * alpha);
-                            tmem_st16(tmem + lane_off + COL_O + c * 16, orr);
+                            tmem_st16(tO + lane_off + c * 16, orr);
                         }
                     }
                 }
-                tmem_st16(tmem + lane_off + COL_P + cc * 16, pk);
+                tmem_st16(tP + lane_off + cc * 16, pk);
             }
-            if constexpr (NP >= 0) {
-                float a0, a1;
-                upk2(add2(rsA, rsB), a0, a1);
-                rs0 = a0; rs1 = a1;
-            }
-            l_run = l_run * alpha + (rs0 + rs1);
+            float a0, a1;
+            upk2(add2(rsA, rsB), a0, a1);
+            l_run = l_run * alpha + (a0 + a1);
+            GD_TR(warp, j, 5);
             tmem_wait_st();
             tc_fence_before();
             if (lane == 0) mbar_arrive(p_full);
+            GD_TR(warp, j, 6);
         }
         // epilogue: O / l -> global fp32, lse
         mbar_wait(pv_done, (nT - 1) & 1);
@@ -253,7 +293,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
 #pragma unroll
         for (int c = 0; c < DV / 16; ++c) {
             uint32_t orr[16];
-            tmem_ld16(tmem + lane_off + COL_O + c * 16, orr);
+            tmem_ld16(tO + lane_off + c * 16, orr);
             tmem_wait_ld();
             float f[16];
 #pragma unroll
@@ -288,7 +328,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
     __syncthreads();
     if (warp == 5) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(C::TMEM_COLS) : "memory");
+        if constexpr (C::SPLIT_ALLOC)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot[1]), "r"(32) : "memory");
     }
 }
 
@@ -408,42 +450,46 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
         }
     } else if (warp == NEW + 1) {
         // ================= MMA issuer =================
+#ifdef GD_MMA_LANE0
         if (lane == 0) {
+#else
+        {   // all 32 lanes walk the loop; one elected lane issues (sm100_util.cuh: umma_*_w)
+#endif
             constexpr uint32_t IDESC_SS = make_idesc(BM, BNK, 0, 0);
             constexpr uint32_t IDESC_DQ = make_idesc(BM, DV, 0, 1);
             const uint32_t aQ = smem_addr(sQ), aDO = smem_addr(sDO);
             auto issue_scores = [&](int j) {
                 const int s = j & 1;
                 const int kst = j % KSTAGE;
-                mbar_wait(k_full + kst, (j / KSTAGE) & 1);
-                mbar_wait(v_full + s, (j >> 1) & 1);
-                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                mbar_wait_mma(k_full + kst, (j / KSTAGE) & 1);
+                mbar_wait_mma(v_full + s, (j >> 1) & 1);
+                if (j > 0) mbar_wait_mma(s_free, (j - 1) & 1);
                 tc_fence_after();
                 const uint32_t aK = smem_addr(sK + kst * K_BYTES), aV = smem_addr(sV + s * K_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks)
-                    umma_ss(tmem + COL_S, make_desc(aQ + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
+                    umma_ss_w(tmem + COL_S, make_desc(aQ + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
                             make_desc(aK + (ks >> 2) * KTILE_BYTES + (ks & 3) * 32, 16, 1024), IDESC_SS, ks > 0);
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks)
-                    umma_ss(tmem + COL_DP, make_desc(aDO + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
+                    umma_ss_w(tmem + COL_DP, make_desc(aDO + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
                             make_desc(aV + (ks >> 2) * KTILE_BYTES + (ks & 3) * 32, 16, 1024), IDESC_SS, ks > 0);
-                tc_commit(s_full);
-                tc_commit(v_empty + s);
+                tc_commit_w(s_full);
+                tc_commit_w(v_empty + s);
             };
-            mbar_wait(q_full, 0);
+            mbar_wait_mma(q_full, 0);
             issue_scores(0);
             for (int j = 0; j < nT; ++j) {
                 if (j + 1 < nT) issue_scores(j + 1);
                 const int s = j % KSTAGE;
-                mbar_wait(ds_full, j & 1);
+                mbar_wait_mma(ds_full, j & 1);
                 tc_fence_after();
                 const uint32_t aK = smem_addr(sK + s * K_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < BNK / 16; ++kk)
-                    umma_ts(tmem + COL_DQ, tmem + COL_DS + kk * 8, make_desc(aK + kk * 2048, KTILE_BYTES, 1024), IDESC_DQ, (j > 0 || kk > 0));
-                tc_commit(dq_done);
-                tc_commit(k_empty + s);
+                    umma_ts_w(tmem + COL_DQ, tmem + COL_DS + kk * 8, make_desc(aK + kk * 2048, KTILE_BYTES, 1024), IDESC_DQ, (j > 0 || kk > 0));
+                tc_commit_w(dq_done);
+                tc_commit_w(k_empty + s);
             }
         }
     } else {
@@ -588,35 +634,34 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
 }
 
 // ---- host side -------------------------------------------------------------------------------------------------------------
-static int g_poly = 4;   // round-1 arithmetic only (g_np < 0): every g_poly-th exponential goes to the FMA pipe
 static int g_bwd_np = 1;
-static int g_np = 2;     // tuning knob (gd_attn_sm100_config): packed arithmetic, g_np of every 8 score pairs on the FMA-pipe polynomial
+static int g_np = 2;     // tuning knob (gd_attn_sm100_config): g_np of every 8 score pairs on the FMA-pipe polynomial
+static int g_bnk = 0;    // keys per step of the forward: 0 = per head_dim (128 at head_dim 40: two CTAs per SM; 64 at head_dim 80: two CTAs per SM
+                         // instead of one, 19.7 against 24.6 us at G=3, N=1024), or 64 / 128 forced (A/B measurements)
 
-template <int D, int POLY, int NP> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
-    constexpr int KB = (D + 63) / 64;
-    const size_t smem = (size_t)5 * KB * 128 * 128 + 256 + 1024;
+template <int D, int BNK, int NP> static int launch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
+    const size_t smem = FwdCfg<D, BNK>::SMEM;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D, POLY, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_fwd_sm100_kernel<D, BNK, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     dim3 grid(p.N / BM, p.H, G);
-    attn_fwd_sm100_kernel<D, POLY, NP><<<grid, SM100_THREADS, smem, st>>>(maps, p);
+    attn_fwd_sm100_kernel<D, BNK, NP><<<grid, SM100_THREADS, smem, st>>>(maps, p);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }
 
-template <int D> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
+template <int D, int BNK> static int dispatch_sm100(const Sm100Maps& maps, const Sm100Params& p, int G, cudaStream_t st) {
     switch (g_np) {
-        case 0: return launch_sm100<D, 0, 0>(maps, p, G, st);
-        case 1: return launch_sm100<D, 0, 1>(maps, p, G, st);
-        case 2: return launch_sm100<D, 0, 2>(maps, p, G, st);
-        case 3: return launch_sm100<D, 0, 3>(maps, p, G, st);
-        case 4: return launch_sm100<D, 0, 4>(maps, p, G, st);
+        case 0: return launch_sm100<D, BNK, 0>(maps, p, G, st);
+        case 1: return launch_sm100<D, BNK, 1>(maps, p, G, st);
+        case 2: return launch_sm100<D, BNK, 2>(maps, p, G, st);
+        case 3: return launch_sm100<D, BNK, 3>(maps, p, G, st);
+        case 4: return launch_sm100<D, BNK, 4>(maps, p, G, st);
     }
-    if (g_np < 0 && g_poly == 4) return launch_sm100<D, 4, -1>(maps, p, G, st);
-    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for poly=%d np=%d", g_poly, g_np);
+    return set_error(GD_ERR_UNSUPPORTED, "gd_attn_sm100_config: no kernel instance for np=%d", g_np);
 }
 
 template <int D, int NP> static int launch_bwd64_sm100(const Sm100BwdMaps& maps, const Sm100BwdParams& p, cudaStream_t st) {
@@ -659,12 +704,13 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
     const long kv_rs = strides ? strides[2] : d, kv_hs = strides ? strides[3] : (long)N * d;
     Sm100Maps maps;
     Sm100Params p;
+    const int bnk = g_bnk ? g_bnk : (d == 40 ? 128 : 64);
     for (int g = 0; g < G; ++g) {
         GD_CHECK_ARG(q[g] && k[g] && v[g] && lse[g] && (o[g] || (os && os[g])));
         int rc;
         if ((rc = make_map(&maps.q[g], q[g], N, H, d, q_rs, q_hs, BM)) != GD_OK) return rc;
-        if ((rc = make_map(&maps.k[g], k[g], N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
-        if ((rc = make_map(&maps.v[g], v[g], N, H, d, kv_rs, kv_hs, BN)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.k[g], k[g], N, H, d, kv_rs, kv_hs, bnk)) != GD_OK) return rc;
+        if ((rc = make_map(&maps.v[g], v[g], N, H, d, kv_rs, kv_hs, bnk)) != GD_OK) return rc;
         p.o[g] = (float*)o[g];
         p.lse[g] = (float*)lse[g];
         p.os[g] = os ? os[g] : nullptr;
@@ -672,19 +718,19 @@ extern "C" int gd_attn_fwd_sm100(const void* const* q, const void* const* k, con
     p.os_rs = strides ? strides[4] : d; p.os_hs = strides ? strides[5] : (long)N * d; p.os_bf16 = os_is_bf16;
     if (os && ((p.os_rs % 8) != 0 || (p.os_hs % 8) != 0)) return set_error(GD_ERR_INVALID, "gd_attn_fwd_sm100: output strides must be multiples of 8");
     p.H = H; p.N = N; p.d = d; p.scale2 = scale * 1.4426950408889634f;
-    if (d == 40) return dispatch_sm100<40>(maps, p, G, (cudaStream_t)stream);
-    return dispatch_sm100<80>(maps, p, G, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (bnk == 64) return d == 40 ? dispatch_sm100<40, 64>(maps, p, G, st) : dispatch_sm100<80, 64>(maps, p, G, st);
+    return d == 40 ? dispatch_sm100<40, 128>(maps, p, G, st) : dispatch_sm100<80, 128>(maps, p, G, st);
 }
 
 // Tuning knobs of the tcgen05 kernels (process-wide; not part of the reference surface).
-//   key 0  fwd: packed fp32x2 softmax arithmetic with `value` in 0..4 of every 8 score pairs on the FMA-pipe polynomial (default 2);
-//               value -1 selects the round-1 scalar arithmetic (A/B measurements), whose polynomial share is key 1
-//   key 1  fwd, scalar arithmetic only: every value-th exponential on the polynomial, value in {0, 4}
+//   key 0  fwd: `value` in 0..4 of every 8 score pairs on the FMA-pipe polynomial (default 2)
+//   key 2  fwd: keys per step: 0 (default: 128 at head_dim 40, 64 at head_dim 80), or 64 / 128 forced
 //   key 3  bwd: value in 0..4 of every 8 score pairs on the polynomial (default 1)
 extern "C" int gd_attn_sm100_config(int key, int value) {
     switch (key) {
-        case 0: if (value < -1 || value > 4) break; g_np = value; return GD_OK;
-        case 1: if (value != 4) break; g_poly = value; return GD_OK;
+        case 0: if (value < 0 || value > 4) break; g_np = value; return GD_OK;
+        case 2: if (value != 0 && value != 64 && value != 128) break; g_bnk = value; return GD_OK;
         case 3: if (value < 0 || value > 4) break; g_bwd_np = value; return GD_OK;
     }
     return set_error(GD_ERR_INVALID, "gd_attn_sm100_config(key=%d, value=%d): see include/geodiffuser_b200.h", key, value);

@@ -110,37 +110,41 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
         }
     } else if (warp == 9) {
         // ================= MMA issuer =================
+        #ifdef GD_MMA_LANE0
         if (lane == 0) {
+#else
+        {   // all 32 lanes walk the loop; one elected lane issues (sm100_util.cuh: umma_*_w)
+#endif
             constexpr uint32_t IDESC_S = make_idesc(CORR_BM, CORR_BK, 0, 0);
             const uint32_t idesc_d = make_idesc(CORR_BM, MC, 0, 0);      // D[n, m] += P[n, k] A_e[m, k]: both operands K-major
             const uint32_t aQ = smem_addr(sQ);
             auto issue_s = [&](int j) {
                 const int s = j % NS;
-                mbar_wait(st_full + s, (j / NS) & 1);
-                if (j > 0) mbar_wait(s_free, (j - 1) & 1);
+                mbar_wait_mma(st_full + s, (j / NS) & 1);
+                if (j > 0) mbar_wait_mma(s_free, (j - 1) & 1);
                 tc_fence_after();
                 const uint32_t aK = smem_addr(sStage + s * STAGE_BYTES);
 #pragma unroll
                 for (int ks = 0; ks < KSTEPS; ++ks)
-                    umma_ss(tmem + COL_S, make_desc(aQ + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
+                    umma_ss_w(tmem + COL_S, make_desc(aQ + (ks >> 2) * QTILE_BYTES + (ks & 3) * 32, 16, 1024),
                             make_desc(aK + (ks >> 2) * KTILE_BYTES + (ks & 3) * 32, 16, 1024), IDESC_S, ks > 0);
-                tc_commit(s_full);
+                tc_commit_w(s_full);
             };
-            mbar_wait(q_full, 0);
+            mbar_wait_mma(q_full, 0);
             issue_s(0);
             for (int j = 0; j < nT; ++j) {
                 if (j + 1 < nT) issue_s(j + 1);
                 const int s = j % NS, b = j & 1;
-                mbar_wait(p_full + b, (j >> 1) & 1);
+                mbar_wait_mma(p_full + b, (j >> 1) & 1);
                 tc_fence_after();
                 const uint32_t aA = smem_addr(sStage + s * STAGE_BYTES + K_BYTES);
 #pragma unroll
                 for (int kk = 0; kk < CORR_BK / 16; ++kk)
-                    umma_ts(tmem + COL_D, tmem + COL_P + b * 32 + kk * 8, make_desc(aA + kk * 32, 16, 1024), idesc_d, (j > 0 || kk > 0));
-                tc_commit(p_free + b);
-                tc_commit(st_empty + s);      // S(j) (issued earlier) and D(j) are both complete when this fires: K and A_e of the stage are free
+                    umma_ts_w(tmem + COL_D, tmem + COL_P + b * 32 + kk * 8, make_desc(aA + kk * 32, 16, 1024), idesc_d, (j > 0 || kk > 0));
+                tc_commit_w(p_free + b);
+                tc_commit_w(st_empty + s);      // S(j) (issued earlier) and D(j) are both complete when this fires: K and A_e of the stage are free
             }
-            tc_commit(d_done);
+            tc_commit_w(d_done);
         }
     } else {
         // ================= softmax warps 0-7: (lane quarter, key half); two threads share a base row n = TMEM lane =================

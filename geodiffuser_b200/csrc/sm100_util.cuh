@@ -29,6 +29,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
 }
+// non-blocking probe: 1 if the phase with this parity has completed.  Issued early, consumed late, it takes the ~120-150 clk that even a
+// satisfied mbarrier wait costs (measured, scripts/fwd_trace.cu) off the issuing warp's critical path.
+__device__ __forceinline__ uint32_t mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t r;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    return r;
+}
 // same, for waits that are not latency critical (the TMA producer runs stages ahead): let the hardware park the thread for up to ~1 us per try
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
     asm volatile(
@@ -38,6 +48,24 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity), "r"(1000u) : "memory");
+}
+// waits of the MMA-issuing warp.  A hot try_wait loop on that warp takes issue slots from the softmax warp that shares its scheduler (measured:
+// that warp runs ~500 clk behind the other three and sets the pace of the tile); parked with a suspend-time hint it does not.
+#ifndef GD_MMA_WAIT_HINT
+#define GD_MMA_WAIT_HINT 200
+#endif
+__device__ __forceinline__ void mbar_wait_mma(uint64_t* bar, uint32_t parity) {
+#if GD_MMA_WAIT_HINT > 0
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity), "r"((uint32_t)GD_MMA_WAIT_HINT) : "memory");
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -56,6 +84,31 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
+// Warp-uniform issue (the MMA warp runs its loop with all 32 lanes; ONE elected lane issues): descriptors and addresses then live in uniform
+// registers.  Issued from inside an `if (lane == 0)` region instead, every tcgen05.mma becomes an ELECT / BRA.U.ANY loop over the active lanes
+// with an R2UR per operand -- ~90 clk per instruction on the issuing thread (measured with scripts/fwd_trace.cu: 770 clk for the 8 MMAs of
+// one P V product, longer than the product itself).
+#ifdef GD_MMA_LANE0     // A/B switch: issue from inside an `if (lane == 0)` region (the form of rounds 1-2a)
+#define tc_commit_w tc_commit
+#define umma_ss_w umma_ss
+#define umma_ts_w umma_ts
+#else
+__device__ __forceinline__ void tc_commit_w(uint64_t* bar) {
+    asm volatile(
+        "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+        "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_ss_w(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, e;\n\telect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "@e tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+#endif
 // D[tmem] (+)= A[smem] * B[smem]
 __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

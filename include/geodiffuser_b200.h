@@ -85,7 +85,7 @@ int gd_attn_fwd_sm100(const void* const* q_host, const void* const* k_host, cons
 
 /* Tuning knobs of the tcgen05 kernels (process-wide, not part of the reference surface).  key 0: forward, `value` in 0..4 of every 8
  * score pairs of the online softmax evaluated by a degree-3 polynomial on the FMA pipe instead of the MUFU (packed fp32x2 arithmetic;
- * default 2; -1 = round-1 scalar arithmetic with key 1 = every value-th exponential on the polynomial, value in {0, 4});
+ * default 2); key 2: forward, keys per step: 0 (default: 128 at head_dim 40, 64 at head_dim 80), or 64 / 128 forced;
  * key 3: polynomial share of the backward kernel (0..4 of 8 pairs, default 1). */
 int gd_attn_sm100_config(int key, int value);
 
