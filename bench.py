@@ -96,10 +96,12 @@ def kernel_traffic(key):
 
 
 def kernel_rooflines(dev, M64, M32, peaks, iters=60):
-    """The dominant kernels of the path, timed EAGERLY in this process at the shapes the edit launches them with (the edit itself replays
-    CUDA graphs, inside which launches cannot carry events): CUDA events on the launching stream around `iters` back-to-back launches
-    after 5 warm-up launches, cycling through enough distinct operand sets that consecutive launches never find their inputs in the
-    126 MB L2.  Algorithmic work per launch: SURVEY 8(d) (forward 4*G*H*N^2*d, backward 6*H*N^2*d, correlation 2*H*M*N^2).
+    """The dominant kernels of the path, timed in this process at the shapes the edit launches them with (the edit itself replays CUDA graphs,
+    inside which single launches cannot carry events).  `iters` back-to-back launches, cycling through enough distinct operand sets that
+    consecutive launches never find their inputs in the 126 MB L2, are recorded into ONE CUDA graph; the graph is replayed once to warm up and
+    once between two CUDA events on the launching stream.  (Launched one by one from Python the host needs 30-45 us per call -- ctypes plus
+    3 G tensor-map encodes -- which is longer than the 32^2-token kernels themselves and used to be counted as kernel time.)
+    Algorithmic work per launch: SURVEY 8(d) (forward 4*G*H*N^2*d, backward 6*H*N^2*d, correlation 2*H*M*N^2, removal dQ rows 2*H*M*N*d).
     Peak: the BURST bf16 figure of MEASURED_PEAKS.json (kernel timed alone); `frac_sustained` uses the sustained one."""
     from geodiffuser_b200 import _lib
     from geodiffuser_b200._lib import call, ptr, stream
@@ -110,13 +112,18 @@ def kernel_rooflines(dev, M64, M32, peaks, iters=60):
     mk = lambda *shape, s=1.5: (torch.randn(*shape, device=dev, generator=gen) * s).bfloat16()
 
     def timed(fns):
-        for i in range(5):
+        for i in range(max(3, len(fns))):
             fns[i % len(fns)]()
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(iters):
+                fns[i % len(fns)]()
+        g.replay()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(iters):
-            fns[i % len(fns)]()
+        g.replay()
         e1.record()
         torch.cuda.synchronize(dev)
         return e0.elapsed_time(e1) / iters
@@ -127,7 +134,7 @@ def kernel_rooflines(dev, M64, M32, peaks, iters=60):
                     avg_launch_ms=ms, launches=iters, algorithmic_flops_per_launch=flops, **extra)
 
     out = []
-    for G, N, d in ((3, 4096, 40), (4, 4096, 40), (3, 1024, 80), (4, 1024, 80)):
+    for G, N, d in ((3, 4096, 40), (4, 4096, 40), (2, 4096, 40), (3, 1024, 80), (4, 1024, 80)):
         nsets = max(2, int(140e6 // ((G + 2) * H * N * d * 2)) + 1)
         fns = []
         for _ in range(nsets):
@@ -141,8 +148,9 @@ def kernel_rooflines(dev, M64, M32, peaks, iters=60):
         out.append(entry("gd_attn_fwd_sm100", f"attn_fwd_sm100_kernel<{d}> G={G} H={H} N={N}", 4.0 * G * H * N * N * d, ms, operand_sets=nsets,
                          traffic=kernel_traffic(f"attn_fwd_sm100_kernel<{d}> G={G} H={H} N={N}")))
         del fns
-    for N, d, M in ((4096, 40, M64), (4096, 40, 0), (1024, 80, M32)):
-        nsets = max(2, int(140e6 // (4 * H * N * d * 2 + M * H * N * 4)) + 1)
+    # backward: the flash term by the tcgen05 kernel; the removal term of the M inpaint rows by its own contraction (gd_removal_dq_rows)
+    for N, d in ((4096, 40), (1024, 80)):
+        nsets = max(2, int(140e6 // (4 * H * N * d * 2)) + 1)
         fns = []
         ld = (N + 7) // 8 * 8
         for _ in range(nsets):
@@ -150,21 +158,41 @@ def kernel_rooflines(dev, M64, M32, peaks, iters=60):
             L = (torch.randn(H, N, device=dev, generator=gen) * 0.1 + 8.0).float()
             delta = torch.randn(H, N, device=dev, generator=gen).float() * 0.01
             dq = torch.empty(H, N, d, device=dev, dtype=torch.float32)
-            extra = rowmap = dl = None
-            Mp = (M + 3) // 4 * 4
-            if M:
-                rows = (torch.arange(M, device=dev) + N // 3).int()      # contiguous rows, like the inpaint set of an object mask
-                rowmap = torch.full((N,), -1, device=dev, dtype=torch.int32)
-                rowmap[rows.long()] = torch.arange(M, device=dev, dtype=torch.int32)
-                extra = torch.randn(H, N, Mp, device=dev, generator=gen) * 0.01     # key-major (gd_removal_extra_rows key_major = 1)
-                dl = torch.ones(1, device=dev)
-            fns.append(lambda q=q, k=k, v=v, do=do, L=L, delta=delta, dq=dq, extra=extra, rowmap=rowmap, dl=dl, N=N, d=d, M=M, Mp=Mp, ld=ld:
-                       call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), ptr(extra), ptr(dl), ptr(rowmap), Mp if M else ld,
-                            M, ptr(dq), H, N, d, float(d ** -0.5), None, 0, 1 if M else 0, stream()))
+            fns.append(lambda q=q, k=k, v=v, do=do, L=L, delta=delta, dq=dq, N=N, d=d, ld=ld:
+                       call("gd_attn_bwd_sm100", ptr(q), ptr(k), ptr(v), ptr(do), ptr(L), ptr(delta), None, None, None, ld, 0, ptr(dq), H, N, d,
+                            float(d ** -0.5), None, 0, 0, stream()))
         ms = timed(fns)
-        out.append(entry("gd_attn_bwd_sm100", f"attn_bwd64_sm100_kernel<{d}> H={H} N={N} removal rows M={M}", 6.0 * H * N * N * d, ms, operand_sets=nsets,
+        out.append(entry("gd_attn_bwd_sm100", f"attn_bwd64_sm100_kernel<{d}> H={H} N={N}", 6.0 * H * N * N * d, ms, operand_sets=nsets,
                          traffic=kernel_traffic(f"attn_bwd64_sm100_kernel<{d}> H={H} N={N}")))
         del fns
+    # removal loss: correlation of attention maps (base map recomputed in TMEM) and the removal rows of dQ, at this edit's inpaint-row counts
+    for N, d, M in ((4096, 40, M64), (4096, 40, 410), (1024, 80, M32)):
+        if M <= 0:
+            continue
+        ld = (N + 7) // 8 * 8
+        nsets = max(2, int(140e6 // (2 * H * N * d * 2 + H * M * ld * 2)) + 1)
+        corr, rowsk = [], []
+        for _ in range(nsets):
+            qb, kb = mk(H, N, d), mk(H, N, d)
+            lse = (torch.randn(H, N, device=dev, generator=gen) * 0.1 + 8.0).float()
+            a_e = (torch.rand(H, M, ld, device=dev, generator=gen) * (2.0 / N)).bfloat16()
+            rows = (torch.arange(M, device=dev) + N // 3).int()
+            m_in = torch.zeros(N, device=dev)
+            m_in[rows.long()] = 1.0
+            m_bg = (1.0 - m_in).contiguous()
+            part = torch.empty(H, N // 32, M, 4, device=dev)
+            dq = torch.zeros(H, N, d, device=dev)
+            gs = torch.ones(1, device=dev)
+            corr.append(lambda qb=qb, kb=kb, lse=lse, a_e=a_e, m_in=m_in, m_bg=m_bg, part=part, N=N, d=d, M=M, ld=ld:
+                        call("gd_removal_corr_sm100", ptr(qb), ptr(kb), ptr(lse), ptr(a_e), H, M, N, d, float(d ** -0.5), ld, None, ptr(m_in), ptr(m_bg),
+                             ptr(part), stream()))
+            rowsk.append(lambda a_e=a_e, kb=kb, rows=rows, gs=gs, dq=dq, N=N, d=d, M=M, ld=ld:
+                         call("gd_removal_dq_rows", ptr(a_e), ptr(kb), ptr(rows), ptr(gs), ptr(dq), H, M, N, N, d, float(d ** -0.5), ld, None, 0, stream()))
+        out.append(entry("gd_removal_corr_sm100", f"removal_corr_sm100_kernel<{d}> H={H} N={N} M={M}", 2.0 * H * M * N * N, timed(corr), operand_sets=nsets,
+                         traffic=kernel_traffic(f"removal_corr_sm100_kernel<{d}> H={H} N={N} M={M}")))
+        out.append(entry("gd_removal_dq_rows", f"removal_dq_rows_kernel<{d}> H={H} N={N} M={M}", 2.0 * H * M * N * d, timed(rowsk), operand_sets=nsets, traffic=None,
+                         note="mma.sync; latency-bound by design (0.2 GFLOP): reported for completeness"))
+        del corr, rowsk
     return out
 
 

@@ -37,6 +37,8 @@ SIGNATURES = {
     "gd_removal_corr_sm100": [P, P, P, P, I, I, I, I, F, I, P, P, P, P, P],
     "gd_attn_probs_rows2": [P, P, P, P, I, I, I, I, I, F, P, I, P, P],
     "gd_removal_extra_rows": [P, P, I, I, I, I, P, I, P],
+    "gd_removal_weighted_rows": [P, P, P, I, I, I, I, P, P],
+    "gd_removal_dq_rows": [P, P, P, P, P, I, I, I, I, I, F, I, P, I, P],
     "gd_attn_l1_losses": [P, P, P, P, P, P, P, F, F, F, F, F, I, I, I, P, P, I, P],
     "gd_removal_finalize": [P, I, I, I, I, P, P, P, F, P, P, I, I, I, P, P, P, P, P, P],
     "gd_loss_reduce": [P, I, P, I, P, P, P, F, P, P, P],

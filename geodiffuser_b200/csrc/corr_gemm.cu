@@ -129,6 +129,149 @@ __global__ void __launch_bounds__(GE_THREADS) gemm_nt_kernel(const GemmParams p)
 
 using namespace gd;
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Removal-loss gradient of the edit queries, as its own small contraction (round 2b).
+//
+// The loss reaches dS through dL/dA_e[h, rows[m], k] = extra[h, m, k] = g_bg A_b[j_bg, k] + g_in A_b[j_in, k] (two base-map rows per inpaint row):
+//   dS = P o (dP - delta)  +  P o extra          ->   dQ = scale dS K = (flash-backward term) + scale (A_e[rows] o extra) K.
+// The second term touches only the M inpaint rows (M ~ 2-10 % of N) and A_e[rows] is already materialised for the correlation, so it is the
+// GEMM  W (M x Nk) @ K (Nk x d)  with W = A_e[rows] o extra: 2 H M Nk d FLOP (0.2 GF at M = 76) instead of 32 extra loads per (row, step) inside the
+// tcgen05 backward, where the few CTAs that own inpaint rows set the makespan of a one-wave grid (96.8 / 84.5 us with M = 410 / 76 rows
+// against 59.7 us without).  delta keeps its removal part (delta_extra, gd_attn_bwd_prep), so the two terms stay independent.
+__global__ void __launch_bounds__(256) removal_weighted_rows_kernel(const bf16* __restrict__ a_e, const bf16* __restrict__ p2, const float2* __restrict__ g,
+                                                                     int H, int M, int Nk, int ld, bf16* __restrict__ w) {
+    const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 2;      // two keys per thread
+    if (i >= (long)H * M * ld) return;
+    const int k = (int)(i % ld);
+    const long hm = i / ld;
+    const int h = (int)(hm / M), m = (int)(hm % M);
+    float v0 = 0.f, v1 = 0.f;
+    if (k < Nk) {
+        const float2 gg = g[hm];
+        const bf16* pa = p2 + ((long)h * 2 * M + m) * ld + k;
+        const bf16* pb = pa + (long)M * ld;
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a_e + i));
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pa));
+        const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pb));
+        v0 = a.x * (gg.x * x.x + gg.y * y.x);
+        v1 = (k + 1 < Nk) ? a.y * (gg.x * x.y + gg.y * y.y) : 0.f;
+    }
+    *reinterpret_cast<__nv_bfloat162*>(w + i) = __floats2bfloat162_rn(v0, v1);
+}
+
+// dq[h, rows[m], :] += (*gscale) * scale * sum_k W[h, m, k] K[h, k, :].  One CTA per (16 inpaint rows, head); its four warps split the keys and
+// meet in shared memory; mma.sync m16n8k16 (A = W chunk via ldmatrix, B = K chunk via ldmatrix.trans).  The arithmetic is negligible (12 MMAs per
+// 32 keys): the kernel is a latency problem, so every warp keeps RQ_STAGES - 1 chunks of 64 keys (K rows + W rows, cp.async) in flight.
+constexpr int RQ_STAGES = 4, RQ_CK = 64, RQ_LDW = RQ_CK + 8;
+template <int D> struct RqCfg {
+    static constexpr int DP = (D + 15) / 16 * 16;          // 48 / 80 accumulator columns
+    static constexpr int LDK = DP + 8;                     // shared row stride of a K chunk (elements): 16-byte aligned rows, conflict-free ldmatrix
+    static constexpr int STAGE = (RQ_CK * LDK + 16 * RQ_LDW) * 2;      // bytes: K chunk + W chunk
+    static constexpr int SMEM = 4 * RQ_STAGES * STAGE;
+};
+template <int D>
+__global__ void __launch_bounds__(128) removal_dq_rows_kernel(const bf16* __restrict__ w, int ld, const bf16* __restrict__ kmat, long k_rs, long k_hs,
+                                                               const int* __restrict__ rows, const float* __restrict__ gscale, float scale, void* dq,
+                                                               long dq_rs, long dq_hs, int dq_bf16, int M, int Nk) {
+    typedef RqCfg<D> C;
+    constexpr int DP = C::DP, LDK = C::LDK, NT = DP / 8, CK = RQ_CK, NST = RQ_STAGES;
+    extern __shared__ __align__(16) unsigned char rq_smem[];
+    float (*red)[16][DP + 1] = reinterpret_cast<float (*)[16][DP + 1]>(rq_smem);       // reuses the rings once every warp is through its keys
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int h = blockIdx.y, m0 = blockIdx.x * 16;
+    const int gq = lane >> 2, tq = lane & 3;
+    const bf16* Kg = kmat + (long)h * k_hs;
+    const bf16* Wg = w + (long)h * M * ld;
+    unsigned char* ring = rq_smem + warp * NST * C::STAGE;
+    auto Kst = [&](int s) { return reinterpret_cast<bf16*>(ring + s * C::STAGE); };
+    auto Wst = [&](int s) { return reinterpret_cast<bf16*>(ring + s * C::STAGE) + CK * LDK; };
+    float acc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f; }
+    // columns D .. LDK-1 of the K chunks feed accumulators that are never stored: zero them once so that they stay finite
+    for (int c = lane; c < NST * CK * (LDK - D); c += 32) {
+        const int s = c / (CK * (LDK - D)), r = (c / (LDK - D)) % CK;
+        Kst(s)[r * LDK + D + c % (LDK - D)] = __float2bfloat16(0.f);
+    }
+    const int per = Nk / 4, kbeg = warp * per, nch = per / CK;       // Nk % 256 == 0
+    constexpr int CPR = D / 8;                      // 16-byte pieces per K row
+    auto issue = [&](int c) {
+        if (c < nch) {
+            const int s = c % NST, k0 = kbeg + c * CK;
+            bf16* kd = Kst(s);
+            bf16* wd = Wst(s);
+            for (int i = lane; i < CK * CPR; i += 32) {
+                const int r = i / CPR, cc = (i % CPR) * 8;
+                cp_async16(kd + r * LDK + cc, Kg + (long)(k0 + r) * k_rs + cc, true);
+            }
+            for (int i = lane; i < 16 * (CK / 8); i += 32) {
+                const int r = i / (CK / 8), cc = (i % (CK / 8)) * 8;
+                const bool ok = m0 + r < M;
+                cp_async16(wd + r * RQ_LDW + cc, Wg + (long)(ok ? m0 + r : 0) * ld + k0 + cc, ok);
+            }
+        }
+        cp_async_commit();                          // (an empty group past the end keeps the wait count uniform)
+    };
+#pragma unroll
+    for (int c = 0; c < NST - 1; ++c) issue(c);
+    for (int c = 0; c < nch; ++c) {
+        issue(c + NST - 1);
+        cp_async_wait<NST - 1>();
+        __syncwarp();
+        const bf16* kc = Kst(c % NST);
+        const bf16* wc = Wst(c % NST);
+#pragma unroll
+        for (int ks = 0; ks < CK; ks += 16) {
+            uint32_t a[4];
+            load_a_frag(a, wc, RQ_LDW, 0, ks, lane);
+#pragma unroll
+            for (int n = 0; n < NT; n += 2) {
+                uint32_t b[4];
+                load_b_frag_nn_x2(b, kc, LDK, ks, n * 8, lane);
+                mma_bf16_16816(acc[n], a, b[0], b[1]);
+                mma_bf16_16816(acc[n + 1], a, b[2], b[3]);
+            }
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+        red[warp][gq][n * 8 + tq * 2] = acc[n][0];
+        red[warp][gq][n * 8 + tq * 2 + 1] = acc[n][1];
+        red[warp][gq + 8][n * 8 + tq * 2] = acc[n][2];
+        red[warp][gq + 8][n * 8 + tq * 2 + 1] = acc[n][3];
+    }
+    __syncthreads();
+    const float f = scale * (gscale ? *gscale : 1.0f);
+    for (int e = tid; e < 16 * D; e += 128) {
+        const int r = e / D, c = e % D, m = m0 + r;
+        if (m >= M) continue;
+        const float v = (red[0][r][c] + red[1][r][c] + red[2][r][c] + red[3][r][c]) * f;     // fixed order: deterministic
+        const long off = (long)h * dq_hs + (long)rows[m] * dq_rs + c;
+        if (dq_bf16) {
+            bf16* o = reinterpret_cast<bf16*>(dq) + off;
+            *o = __float2bfloat16(__bfloat162float(*o) + v);
+        } else {
+            reinterpret_cast<float*>(dq)[off] += v;
+        }
+    }
+}
+
+template <int D> static int launch_removal_dq_rows(dim3 grid, cudaStream_t st, const bf16* w, int ld, const bf16* k, long k_rs, long k_hs, const int* rows,
+                                                   const float* gscale, float scale, void* dq, long dq_rs, long dq_hs, int dq_bf16, int M, int Nk) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(removal_dq_rows_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, RqCfg<D>::SMEM);
+        if (e != cudaSuccess) return set_error(GD_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    removal_dq_rows_kernel<D><<<grid, 128, RqCfg<D>::SMEM, st>>>(w, ld, k, k_rs, k_hs, rows, gscale, scale, dq, dq_rs, dq_hs, dq_bf16, M, Nk);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
 extern "C" {
 
 // P[h, m, :] = softmax row of q[h, rows[m] (or m), :] against k[h] given its natural-log lse; bf16 out, row stride ldp
@@ -179,6 +322,32 @@ int gd_corr_max_partial(const void* a_e, const void* a_b, int H, int M, int Nb, 
     gemm_nt_kernel<1><<<grid, GE_THREADS, 0, (cudaStream_t)stream>>>(p);
     GD_CHECK_LAUNCH();
     return GD_OK;
+}
+
+// W[h, m, k] = A_e[h, m, k] * (g2[h,m].x * P2[h, m, k] + g2[h,m].y * P2[h, M + m, k])  (bf16, (H, M, ld), zero past Nk): the removal term's dS rows
+int gd_removal_weighted_rows(const void* a_e, const void* p2, const float* g2, int H, int M, int Nk, int ld, void* w_bf16, void* stream) {
+    GD_CHECK_ARG(a_e && p2 && g2 && w_bf16 && H > 0 && M > 0 && Nk > 0 && ld >= Nk && ld % 2 == 0);
+    const long n = ((long)H * M * ld + 1) / 2;
+    removal_weighted_rows_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)a_e, (const bf16*)p2, (const float2*)g2, H, M, Nk, ld, (bf16*)w_bf16);
+    GD_CHECK_LAUNCH();
+    return GD_OK;
+}
+
+// dq[h, rows[m], :] += (*gscale) * scale * sum_k W[h, m, k] K[h, k, :]   (the removal-loss part of dQ; see removal_dq_rows_kernel).
+// k: slab with strides_host = {kv_row, kv_head, dq_row, dq_head} (NULL: contiguous (H, Nk, d) / (H, N, d)); dq fp32 or bf16, accumulated in place.
+int gd_removal_dq_rows(const void* w_bf16, const void* k, const int* rows, const float* gscale, void* dq, int H, int M, int N, int Nk, int d, float scale,
+                       int ld, const long* strides, int dq_is_bf16, void* stream) {
+    GD_CHECK_ARG(w_bf16 && k && rows && dq && H > 0 && M > 0 && N > 0 && ld >= Nk && ld % 8 == 0);
+    if (!((d == 40 || d == 80) && Nk % 256 == 0))
+        return set_error(GD_ERR_UNSUPPORTED, "gd_removal_dq_rows serves d in {40, 80}, Nk %% 256 == 0; got d=%d Nk=%d", d, Nk);
+    const long k_rs = strides ? strides[0] : d, k_hs = strides ? strides[1] : (long)Nk * d;
+    const long dq_rs = strides ? strides[2] : d, dq_hs = strides ? strides[3] : (long)N * d;
+    if ((k_rs % 8) != 0 || (k_hs % 8) != 0 || (reinterpret_cast<uintptr_t>(k) & 15) != 0)
+        return set_error(GD_ERR_INVALID, "gd_removal_dq_rows: k base and strides must be 16-byte aligned");
+    dim3 grid(ceil_div(M, 16), H);
+    cudaStream_t st = (cudaStream_t)stream;
+    return d == 40 ? launch_removal_dq_rows<40>(grid, st, (const bf16*)w_bf16, ld, (const bf16*)k, k_rs, k_hs, rows, gscale, scale, dq, dq_rs, dq_hs, dq_is_bf16, M, Nk)
+                   : launch_removal_dq_rows<80>(grid, st, (const bf16*)w_bf16, ld, (const bf16*)k, k_rs, k_hs, rows, gscale, scale, dq, dq_rs, dq_hs, dq_is_bf16, M, Nk);
 }
 
 }  // extern "C"

@@ -34,12 +34,12 @@ struct CorrParams {
     const float* lse;             // (H, N) natural log
     const float* mask_in; const float* mask_bg;   // (N)
     float4* partial;              // (H, 4 * N/128, M)
-    int H, N, M, MC, n_stage;
+    int H, N, M, MC, n_stage, tmem_cols;
     float scale2;
 };
 
 template <int D>
-__global__ void __launch_bounds__(CORR_THREADS, 1)
+__global__ void __launch_bounds__(CORR_THREADS, 2)
 removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParams p) {
     constexpr int KB = (D + 63) / 64;
     constexpr int KSTEPS = (D + 15) / 16;
@@ -47,7 +47,6 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
     constexpr int KTILE_BYTES = CORR_BK * 128;             // [64 keys][64 bf16] block of K_b
     constexpr int Q_BYTES = KB * QTILE_BYTES, K_BYTES = KB * KTILE_BYTES;
     constexpr uint32_t COL_S = 0, COL_P = 64, COL_D = 128;
-    constexpr int TMEM_COLS = 512;
     constexpr int MAX_STAGE = 4;
 
     extern __shared__ unsigned char smem_dyn[];
@@ -82,7 +81,7 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(tmem_slot)), "r"(p.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 8 && lane == 0) { tma_prefetch_desc(&maps.q); tma_prefetch_desc(&maps.k); tma_prefetch_desc(&maps.a); }
@@ -223,7 +222,7 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
     __syncthreads();
     if (warp == 9) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(p.tmem_cols) : "memory");
     }
 }
 
@@ -273,7 +272,13 @@ extern "C" int gd_removal_corr_sm100(const void* q_b, const void* k_b, const flo
     p.H = H; p.N = N; p.M = M; p.MC = MC; p.scale2 = scale * 1.4426950408889634f;
     const int kb = (d + 63) / 64;
     const int stage = (kb * CORR_BK * 128 + MC * 128 + 1023) & ~1023;
-    p.n_stage = (int)((184 * 1024 - kb * 128 * 128) / stage);
+    // S 64 + P 2 x 32 + D MC columns: chunks of up to 128 inpaint rows fit 256 TMEM columns, i.e. TWO CTAs per SM (the strictly sequential
+    // S -> exp -> P -> D chain of one CTA leaves both pipes idle most of the time; with the bench edit's M = 76 the 256 CTAs of a 64^2 layer then
+    // also run as one wave instead of two).  Shared memory is budgeted accordingly.
+    const int fixed = kb * 128 * 128 + 8 * 32 * 33 * 4 + 256 + 1024;      // Q tile, epilogue transpose tiles, barriers, alignment
+    bool two = MC <= 128 && (112 * 1024 - fixed) / stage >= 2;
+    p.tmem_cols = two ? 256 : 512;
+    p.n_stage = two ? (112 * 1024 - fixed) / stage : (int)((184 * 1024 - kb * 128 * 128) / stage);
     if (p.n_stage > 4) p.n_stage = 4;
     if (p.n_stage < 2) return set_error(GD_ERR_UNSUPPORTED, "gd_removal_corr_sm100: stage of %d bytes does not fit twice", stage);
     if (d == 40) return launch_corr<40>(maps, p, n_chunks, (cudaStream_t)stream);

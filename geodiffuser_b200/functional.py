@@ -15,6 +15,7 @@ from . import _lib, geometry
 from ._lib import call, ptr, stream
 
 TERM_NAMES = ("sim", "movement", "removal", "smoothness", "amodal")
+REMOVAL_DQ_GEMM = True   # removal term of dQ as its own (M x Nk) @ (Nk x d) contraction after the tcgen05 backward (False: `extra` rows folded into that kernel)
 CORR_SM100 = True   # removal-loss correlation of the self-attention levels on the tcgen05 kernel (False: materialised base map + mma.sync, for A/B tests)
 
 
@@ -325,10 +326,17 @@ def _forward_impl(q, k, v, spec, proj=False):
             p2 = torch.empty(h, 2 * M, ld, device=dev, dtype=torch.bfloat16)
             call("gd_attn_probs_rows2", bp(sl(qb, cb0)), bp(sl(kb, cb0)), ptr(LSE[cb0]), ptr(j2), M, h, N, Nk, d, float(spec.scale), ptr(p2), ld,
                  qk_st, stream())
-            # dL/dA_e rows, key-major (H, Nk, Mp): the layout the tcgen05 backward reads coalesced
-            ex_key_major, ex_ld = 1, (M + 3) // 4 * 4
-            extra = torch.empty(h, Nk, ex_ld, device=dev, dtype=torch.float32)
-            call("gd_removal_extra_rows", ptr(p2), ptr(g2), h, M, Nk, ld, ptr(extra), 1, stream())
+            if REMOVAL_DQ_GEMM and Nk % 256 == 0:
+                # the removal term of dS lives on the M inpaint rows only: W = A_e[rows] o dL/dA_e[rows] (bf16), contracted with K after the
+                # tcgen05 backward (gd_removal_dq_rows), which then runs without `extra`
+                ex_key_major, ex_ld = 2, ld
+                extra = torch.empty(h, M, ld, device=dev, dtype=torch.bfloat16)
+                call("gd_removal_weighted_rows", ptr(a_e), ptr(p2), ptr(g2), h, M, Nk, ld, ptr(extra), stream())
+            else:
+                # dL/dA_e rows, key-major (H, Nk, Mp): the layout the tcgen05 backward reads coalesced
+                ex_key_major, ex_ld = 1, (M + 3) // 4 * 4
+                extra = torch.empty(h, Nk, ex_ld, device=dev, dtype=torch.float32)
+                call("gd_removal_extra_rows", ptr(p2), ptr(g2), h, M, Nk, ld, ptr(extra), 1, stream())
             del p2
         else:
             # cross layers (Nk = 77) and ragged shapes: materialise the base map (bf16, H x N x ld: 5 MB at Nk = 77) and correlate with mma.sync
@@ -462,9 +470,16 @@ class _SharedAttentionLayerFn(torch.autograd.Function):
         dq_is_bf16 = int(q_dtype == torch.bfloat16)
         ex_ld, ex_km = (s["ex_ld"], s["ex_key_major"]) if has_extra else (s["ld"], 0)
         if _lib.HAS_SM100 and Nk == N and N % 128 == 0 and d in (40, 80) and N >= 1024 and s["ld"] % 4 == 0:
-            call("gd_attn_bwd_sm100", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
-                 ptr(d_loss) if has_extra else None, rowmap, ex_ld, M, bp(lay.sl(dq, ce0)), h, N, d, float(spec.scale), lay.strides(), dq_is_bf16,
-                 ex_km, stream(), tag=(h, N, N, d))
+            if has_extra and ex_km == 2:
+                # flash-backward term by the tcgen05 kernel, removal term (inpaint rows only) by its own contraction on top of it
+                call("gd_attn_bwd_sm100", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), None, None, None, s["ld"], 0,
+                     bp(lay.sl(dq, ce0)), h, N, d, float(spec.scale), lay.strides(), dq_is_bf16, 0, stream(), tag=(h, N, N, d))
+                call("gd_removal_dq_rows", extra, bp(s["k_e"]), ptr(spec.cache.rows), ptr(d_loss), bp(lay.sl(dq, ce0)), h, M, N, Nk, d, float(spec.scale),
+                     ex_ld, _lib.host_longs([lay.kv[0], lay.kv[1], lay.q[0], lay.q[1]]), dq_is_bf16, stream())
+            else:
+                call("gd_attn_bwd_sm100", bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,
+                     ptr(d_loss) if has_extra else None, rowmap, ex_ld, M, bp(lay.sl(dq, ce0)), h, N, d, float(spec.scale), lay.strides(), dq_is_bf16,
+                     ex_km, stream(), tag=(h, N, N, d))
         else:
             assert ex_km == 0
             call("gd_attn_bwd", 0, bp(s["q_e"]), bp(s["k_e"]), bp(s["v_e"]), ptr(d_o), ptr(s["lse_e"]), ptr(delta), extra,

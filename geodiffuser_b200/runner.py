@@ -67,7 +67,16 @@ class EditWorkers:
             t.start()
 
     def _lane(self, w):
+        from . import graphs
+
         torch.cuda.set_device(self.device)
+        # cuBLAS / cuDNN handles are per host thread and created on first use (cublasCreate allocates and synchronises): create this thread's
+        # now, under the capture lock, so that it never happens while another lane records a graph (that capture would be invalidated)
+        with graphs._CAPTURE_LOCK, torch.cuda.stream(self.streams[w]), torch.no_grad():
+            a = torch.ones(8, 8, device=self.device, dtype=torch.bfloat16)
+            (a @ a).float() @ torch.ones(8, 8, device=self.device)
+            torch.nn.functional.conv2d(a.reshape(1, 1, 8, 8), torch.ones(1, 1, 3, 3, device=self.device, dtype=torch.bfloat16), padding=1)
+            self.streams[w].synchronize()
         while True:
             job = self._jobs[w].get()
             if job is None:

@@ -149,6 +149,14 @@ int gd_attn_probs_rows2(const void* q, const void* k, const float* lse, const in
  * key_major = 1: transposed, (H, Nk, Mp) fp32 with Mp = M rounded up to 4 -- the layout gd_attn_bwd_sm100 reads coalesced. */
 int gd_removal_extra_rows(const void* p2_bf16, const float* g2, int H, int M, int Nk, int ld, float* extra, int key_major, void* stream);
 
+/* The removal term of dQ as its own contraction (self-attention levels): dS gets P o extra on the M inpaint rows only, and A_e[rows] is already
+ * materialised, so  dq[h, rows[m], :] += (*gscale) * scale * sum_k W[h,m,k] K[h,k,:]  with  W = A_e[rows] o (g_bg P2[m] + g_in P2[M+m])  (bf16 (H,M,ld)).
+ * Replaces the dense `dcorr . A_b` autograd forms at attention_processors.py:262-280; gd_attn_bwd_sm100 then runs without `extra`.
+ * strides_host = {kv_row, kv_head, dq_row, dq_head} (NULL: contiguous); d in {40, 80}, Nk % 256 == 0; dq (fp32 / bf16) is accumulated in place. */
+int gd_removal_weighted_rows(const void* a_e_bf16, const void* p2_bf16, const float* g2, int H, int M, int Nk, int ld, void* w_bf16, void* stream);
+int gd_removal_dq_rows(const void* w_bf16, const void* k, const int* rows, const float* gscale, void* dq, int H, int M, int N, int Nk, int d,
+                       float scale, int ld, const long* strides_host, int dq_is_bf16, void* stream);
+
 /* attention_processors.py:231-246 (sim), 283-287 (movement), 289-305 (amodal, target t), loss.py:22-41 (smoothness): unweighted partial
  * sums (n_partials,5) and grad = d(weighted loss)/d replace_out.  c_* = weight / denominator of each term. */
 int gd_attn_l1_losses(const float* e, const float* r, const float* t, const float* m_bg, const float* m_edit, const float* m_am,

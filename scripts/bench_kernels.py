@@ -151,6 +151,32 @@ def corr_case(H, N, d, M):
           f"(mma.sync path: {rel(oi, ri):.2e} {rel(ob, rb):.2e})", flush=True)
 
 
+def rows_case(H, N, d, M):
+    """removal term of dQ as its own contraction: W = A_e[rows] o (g_bg P2[m] + g_in P2[M+m]), dq[rows] += gscale * scale * W @ K"""
+    g = torch.Generator(device="cuda").manual_seed(N + d + M)
+    ld = (N + 7) // 8 * 8
+    a_e = torch.rand(H, M, ld, device="cuda", generator=g).bfloat16() * 0.01
+    p2 = torch.rand(H, 2 * M, ld, device="cuda", generator=g).bfloat16() * 0.01
+    g2 = torch.randn(H * M, 2, device="cuda", generator=g)
+    k = mk(g, H, N, d)
+    rows = (torch.arange(M, device="cuda") + N // 3).int()
+    gs = torch.full((1,), 0.7, device="cuda")
+    w = torch.empty(H, M, ld, device="cuda", dtype=torch.bfloat16)
+    dq = torch.zeros(H, N, d, device="cuda")
+    scale = d ** -0.5
+    f_w = lambda: call("gd_removal_weighted_rows", ptr(a_e), ptr(p2), ptr(g2), H, M, N, ld, ptr(w), stream())
+    f_d = lambda: call("gd_removal_dq_rows", ptr(w), ptr(k), ptr(rows), ptr(gs), ptr(dq), H, M, N, N, d, float(scale), ld, None, 0, stream())
+    ms_w, ms_d = timed(f_w, iters), timed(f_d, iters)
+    dq.zero_()
+    f_w(); f_d()
+    gg = g2.reshape(H, M, 2)
+    wr = a_e.float() * (gg[..., :1] * p2[:, :M].float() + gg[..., 1:] * p2[:, M:].float())
+    ref = torch.einsum("hmk,hkd->hmd", wr[:, :, :N], k.float()) * scale * 0.7
+    got = dq[:, rows.long(), :]
+    print(f"removal dQ rows        H={H} N={N:5d} d={d:3d} M={M:4d}: weighted rows {ms_w * 1e3:6.1f} us + W@K {ms_d * 1e3:6.1f} us  relerr {rel(got, ref):.2e}  "
+          f"(rows outside the set untouched: {bool((dq.abs().sum((0, 2)) > 0).sum() == M)})", flush=True)
+
+
 cfg = lambda key, value: call("gd_attn_sm100_config", key, value)
 
 if only in ("corr", "sweep"):
@@ -158,6 +184,13 @@ if only in ("corr", "sweep"):
     corr_case(8, 4096, 40, 76)
     corr_case(8, 4096, 40, 640)
     corr_case(8, 1024, 80, 100)
+
+if only == "rows":
+    rows_case(8, 4096, 40, 76)
+    rows_case(8, 4096, 40, 410)
+    rows_case(8, 1024, 80, 18)
+    rows_case(8, 1024, 80, 100)
+    rows_case(2, 9216, 40, 900)
 
 if only == "ab":
     for bnk in (128, 64):

@@ -312,12 +312,18 @@ def test_concurrent_edit_lanes_preserve_every_edit():
         tiny_model = unet_sd15.build_model("cuda", tiny=True)      # (a fresh one: every graph of this test is recorded under the heuristic choice)
         torch.backends.cudnn.benchmark = False
         kinds = ["rotate3d", "remove", "translate2d", "rotate3d", "remove", "translate2d"]
-        alone = {k: editor.perform_synthetic_edit(tiny_model, k, num_ddim_steps=6).float().cpu() for k in set(kinds)}
-        alone = {k: editor.perform_synthetic_edit(tiny_model, k, num_ddim_steps=6).float().cpu() for k in set(kinds)}    # second round: graphs replayed
+        # the single-lane baseline runs on a fresh host thread as well: cuDNN keeps its plan caches per thread, and the main thread of a test
+        # session still holds the autotuned plans of earlier tests for these very shapes (it would keep using them with benchmark off)
+        one = runner.EditWorkers(tiny_model, lanes=1)
+        fn = lambda m, k: editor.perform_synthetic_edit(m, k, num_ddim_steps=6)
+        for _ in range(2):                                      # second round: graphs replayed
+            alone = {k: one.map(fn, [k])[0].float().cpu() for k in sorted(set(kinds))}
+        torch.cuda.synchronize()
+        one.close()
         workers = runner.EditWorkers(tiny_model, lanes=2)
         assert workers.models[1].unet is not tiny_model.unet
         assert all(a is b for a, b in zip(workers.models[1].unet.parameters(), tiny_model.unet.parameters()))     # weights shared, not copied
-        for round_ in range(2):
+        for round_ in range(3):
             outs = workers.map(lambda m, k: editor.perform_synthetic_edit(m, k, num_ddim_steps=6), kinds)
             torch.cuda.synchronize()
             for k, o in zip(kinds, outs):
@@ -326,7 +332,10 @@ def test_concurrent_edit_lanes_preserve_every_edit():
                 p = psnr(o[1].numpy(), alone[k][1].numpy())
                 print(f"round {round_} {k}: edited latent vs the same edit alone: PSNR {p:.1f} dB")
                 assert torch.equal(o[0], alone[k][0])          # the reference sample (inversion trajectory): gradient-free graphs are bit-exact
-                assert p >= 45.0
+                # round 0 is each lane's warm-up: the first optimisation pass of a kind on a lane runs eagerly (then is recorded), and the eager
+                # evaluation of the body may use other cuBLAS / cuDNN algorithms than the recorded one (test_graphed_gradient_pass_matches_eager);
+                # the removal edit amplifies that to ~34 dB.  From round 1 on every pass is a replay, as in the single-lane run it is compared with.
+                assert p >= (45.0 if round_ > 0 else 25.0)
         workers.close()
     finally:
         torch.backends.cudnn.benchmark = bench
