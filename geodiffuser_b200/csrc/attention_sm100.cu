@@ -69,6 +69,7 @@ template <int D, int BNK> struct FwdCfg {
     static constexpr uint32_t COL_S = 0;
     static constexpr uint32_t COL_O = SPLIT_ALLOC ? 64 : (BNK == 64 ? 96 : 192);
     static constexpr uint32_t COL_P = SPLIT_ALLOC ? 0 : (BNK == 64 ? 64 : 128);      // SPLIT_ALLOC: relative to the second allocation
+    static constexpr bool ONES = DV > D;             // head_dim 40: column 40 of the zero-filled V padding is set to 1, so that O[:, 40] = row sum of P
     static constexpr int KB = (D + 63) / 64;
     static constexpr size_t SMEM = (size_t)KB * 128 * 128 + (size_t)NSTAGE * 2 * KB * BNK * 128 + 256 + 1024;
 };
@@ -84,6 +85,11 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
     constexpr int KTILE_BYTES = BNK * 128;          // one [BNK rows][64 bf16] swizzled block of K / V
     constexpr int Q_BYTES = KB * QTILE_BYTES, K_BYTES = KB * KTILE_BYTES;
     constexpr int NSTAGE = C::NSTAGE;
+#ifdef GD_FWD_NOPROBE
+    constexpr bool PROBE = false;
+#else
+    constexpr bool PROBE = true;
+#endif
 
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -100,7 +106,8 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
     uint64_t* k_empty = k_full + NSTAGE;
     uint64_t* v_full = k_empty + NSTAGE;
     uint64_t* v_empty = v_full + NSTAGE;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + NSTAGE);   // [2]
+    uint64_t* v_tma = v_empty + NSTAGE;           // [NSTAGE]  (ONES: the V tile has landed; v_full follows once its ones column is written)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_tma + NSTAGE);   // [2]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.z, h = blockIdx.y, q0 = blockIdx.x * BM;
@@ -109,7 +116,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(k_full + s, 1); mbar_init(k_empty + s, 1); mbar_init(v_full + s, 1); mbar_init(v_empty + s, 1); mbar_init(v_tma + s, 1); }
         mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4); mbar_init(pv_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -128,11 +135,28 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
 
     if (warp == 4) {
         // ================= TMA producer (runs up to NSTAGE stages ahead: its waits are not latency critical) =================
+        // ONES (head_dim 40): TMA zero-fills columns 40..63 of every V row; the producer warp then writes 1.0 into column 40 of the landed tile, so
+        // that the P V product accumulates the row sum of P in O[:, 40] -- the softmax warps do not add up their exponentials (64 FADD2 per row
+        // and tile less on the warps that bound the kernel), and numerator and denominator see the same bf16-rounded P.
+        auto patch_v = [&](int j) {
+            const int s = j % NSTAGE;
+            mbar_wait_relaxed(v_tma + s, (j / NSTAGE) & 1);
+            unsigned char* vt = sV + s * K_BYTES + (D / 64) * KTILE_BYTES;
+            constexpr int CH = ((D % 64) * 2) / 16, OFF = ((D % 64) * 2) % 16;       // 16-byte chunk of column D inside its 128-byte row, SWIZZLE_128B
+#pragma unroll
+            for (int r = lane; r < BNK; r += 32)
+                *reinterpret_cast<unsigned short*>(vt + r * 128 + ((CH ^ (r & 7)) * 16) + OFF) = 0x3F80;     // bf16 1.0
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic-proxy stores -> visible to the tensor core's reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(v_full + s);
+        };
         if (lane == 0) {
             mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
             for (int b = 0; b < KB; ++b) tma_load_3d(sQ + b * QTILE_BYTES, &maps.q[g], q_full, b * 64, q0, h);
-            for (int j = 0; j < nT; ++j) {
+        }
+        for (int j = 0; j < nT; ++j) {
+            if (lane == 0) {
                 const int s = j % NSTAGE;
                 const uint32_t ph = (j / NSTAGE) & 1;
                 mbar_wait_relaxed(k_empty + s, ph ^ 1);
@@ -142,11 +166,15 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
                 for (int b = 0; b < KB; ++b) tma_load_3d(sK + s * K_BYTES + b * KTILE_BYTES, &maps.k[g], k_full + s, b * 64, j * BNK, h);
                 mbar_wait_relaxed(v_empty + s, ph ^ 1);
                 GD_TR(5, j, 1);
-                mbar_expect_tx(v_full + s, K_BYTES);
+                uint64_t* vb = C::ONES ? v_tma + s : v_full + s;
+                mbar_expect_tx(vb, K_BYTES);
 #pragma unroll
-                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * K_BYTES + b * KTILE_BYTES, &maps.v[g], v_full + s, b * 64, j * BNK, h);
+                for (int b = 0; b < KB; ++b) tma_load_3d(sV + s * K_BYTES + b * KTILE_BYTES, &maps.v[g], vb, b * 64, j * BNK, h);
             }
+            __syncwarp();
+            if (C::ONES && j > 0) patch_v(j - 1);     // V(j-1) landed a step ago; P V(j-1) is issued at the end of softmax(j-1): far off the critical path
         }
+        if (C::ONES) patch_v(nT - 1);
     } else if (warp == 5) {
         // ================= MMA issuer =================
 #ifdef GD_MMA_LANE0
@@ -200,14 +228,18 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
         const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         const float scale2 = p.scale2;
         float m_run = -INFINITY, l_run = 0.f;
+        uint32_t s_ready = 0;                        // probe of s_full(j), issued during step j-1
         for (int j = 0; j < nT; ++j) {
             GD_TR(warp, j, 0);
-            mbar_wait(s_full, j & 1);
+            if (!s_ready) mbar_wait(s_full, j & 1);
             GD_TR(warp, j, 1);
             tc_fence_after();
             uint32_t sr[BNK];
 #pragma unroll
             for (int c = 0; c < BNK / 32; ++c) tmem_ld32(tS + lane_off + c * 32, sr + c * 32);
+            // pv_done(j-1) is needed after the first chunk of exponentials: probe it now, so that the ~120 clk even a satisfied mbarrier wait
+            // costs (scripts/fwd_trace.cu) run under the row max and that chunk instead of stalling the warp there
+            const uint32_t pv_ready = (PROBE && j > 0) ? mbar_test(pv_done, (j - 1) & 1) : 0u;
             tmem_wait_ld();
             tc_fence_before();
             if (lane == 0) mbar_arrive(s_free);      // S(j) is in registers: QK^T(j+1) may overwrite it
@@ -227,8 +259,9 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
             const float m_new = grow ? m_cand : m_run;
             const float alpha = grow ? ex2(m_run - m_new) : 1.0f;
             m_run = m_new;
-            u64 rsA = 0ull, rsB = 0ull;                           // packed row-sum accumulators (two chains)
+            u64 rsA = 0ull, rsB = 0ull;                           // packed row-sum accumulators (two chains); unused with the ones column
             const u64 sc2 = pk2(scale2, scale2), nm2 = pk2(-m_new, -m_new);
+            s_ready = 0;
 #pragma unroll
             for (int cc = 0; cc < BNK / 32; ++cc) {
                 uint32_t pk[16];
@@ -248,7 +281,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
                         p1 = ex2(x1);
                         p2 = pk2(p0, p1);
                     }
-                    if (c & 1) rsB = add2(rsB, p2); else rsA = add2(rsA, p2);
+                    if constexpr (!C::ONES) { if (c & 1) rsB = add2(rsB, p2); else rsA = add2(rsA, p2); }
                     __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
                     pk[c] = *reinterpret_cast<uint32_t*>(&b2);
                 }
@@ -257,7 +290,7 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
                     // exponentials after the row max -- instead of in front of the exponentials keeps the MMA round trip
                     // (p_full -> PV issue -> commit) off the softmax warps' critical path.
                     GD_TR(warp, j, 3);
-                    mbar_wait(pv_done, (j - 1) & 1);
+                    if (!pv_ready) mbar_wait(pv_done, (j - 1) & 1);
                     GD_TR(warp, j, 4);
                     tc_fence_after();
                     if (__any_sync(0xffffffffu, grow)) {
@@ -272,11 +305,14 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
                         }
                     }
                 }
+                if (PROBE && cc == BNK / 32 - 1 && j + 1 < nT) s_ready = mbar_test(s_full, (j + 1) & 1);   // consumed at the top of step j+1
                 tmem_st16(tP + lane_off + cc * 16, pk);
             }
-            float a0, a1;
-            upk2(add2(rsA, rsB), a0, a1);
-            l_run = l_run * alpha + (a0 + a1);
+            if constexpr (!C::ONES) {
+                float a0, a1;
+                upk2(add2(rsA, rsB), a0, a1);
+                l_run = l_run * alpha + (a0 + a1);
+            }
             GD_TR(warp, j, 5);
             tmem_wait_st();
             tc_fence_before();
@@ -287,6 +323,12 @@ attn_fwd_sm100_kernel(const __grid_constant__ Sm100Maps maps, const Sm100Params 
         mbar_wait(pv_done, (nT - 1) & 1);
         tc_fence_after();
         const int row = q0 + warp * 32 + lane;
+        if constexpr (C::ONES) {                     // the row sum sits in O[:, D] (it took part in every lazy rescale of O)
+            uint32_t orr[16];
+            tmem_ld16(tO + lane_off + (D / 16) * 16, orr);
+            tmem_wait_ld();
+            l_run = __uint_as_float(orr[D % 16]);
+        }
         const float inv = 1.0f / l_run;
         float* og = p.o[g] ? p.o[g] + ((long)h * N + row) * D : nullptr;
         unsigned char* sg = p.os[g] ? reinterpret_cast<unsigned char*>(p.os[g]) + ((long)h * p.os_hs + (long)row * p.os_rs) * (p.os_bf16 ? 2 : 4) : nullptr;
@@ -422,7 +464,7 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == NEW) {
         // ================= TMA producer =================
@@ -525,12 +567,14 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
             return *reinterpret_cast<uint32_t*>(&b2);
         };
         if (!any_ex) {
+            uint32_t s_ready = 0;                                 // probe of s_full(j), issued during step j-1 (see the forward kernel)
             for (int j = 0; j < nT; ++j) {
-                mbar_wait(s_full, j & 1);
+                if (!s_ready) mbar_wait(s_full, j & 1);
                 tc_fence_after();
                 uint32_t sr[NC], dp[NC];
                 tmem_ld32(tmem + lane_off + COL_S + half * NC, sr);
                 tmem_ld32(tmem + lane_off + COL_DP + half * NC, dp);
+                const uint32_t dq_ready = j > 0 ? mbar_test(dq_done, (j - 1) & 1) : 0u;     // needed only after the step's arithmetic
                 tmem_wait_ld();
                 tc_fence_before();
                 if (lane == 0) mbar_arrive(s_free);
@@ -538,9 +582,10 @@ attn_bwd64_sm100_kernel(const __grid_constant__ Sm100BwdMaps maps, const Sm100Bw
 #pragma unroll
                 for (int c = 0; c < NC / 2; ++c) pk[c] = ds_pair(sr[2 * c], sr[2 * c + 1], dp[2 * c], dp[2 * c + 1], c);
                 if (j > 0) {
-                    mbar_wait(dq_done, (j - 1) & 1);              // dS(j-1) has been consumed by its dQ product
+                    if (!dq_ready) mbar_wait(dq_done, (j - 1) & 1);              // dS(j-1) has been consumed by its dQ product
                     tc_fence_after();
                 }
+                s_ready = (j + 1 < nT) ? mbar_test(s_full, (j + 1) & 1) : 0u;
                 tmem_st16(tmem + lane_off + COL_DS + half * (NC / 2), pk);
                 tmem_wait_st();
                 tc_fence_before();

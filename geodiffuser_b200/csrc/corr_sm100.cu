@@ -88,7 +88,7 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot;
+    const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 8) {
         // ================= TMA producer =================
@@ -152,15 +152,17 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
         const int n = n0 + quarter * 32 + lane;
         const float lse2 = p.lse[(long)h * N + n] * 1.4426950408889634f;
         const u64 sc2 = pk2(p.scale2, p.scale2), nl2 = pk2(-lse2, -lse2);
+        uint32_t s_ready = 0;                                     // probe of s_full(j), issued during step j-1 (see attention_sm100.cu)
         for (int j = 0; j < nT; ++j) {
-            mbar_wait(s_full, j & 1);
+            if (!s_ready) mbar_wait(s_full, j & 1);
             tc_fence_after();
             uint32_t sr[32];
             tmem_ld32(tmem + lane_off + COL_S + half * 32, sr);
+            const int b = j & 1;
+            const uint32_t pf_ready = j >= 2 ? mbar_test(p_free + b, ((j - 2) >> 1) & 1) : 0u;
             tmem_wait_ld();
             tc_fence_before();
             if (lane == 0) mbar_arrive(s_free);
-            const int b = j & 1;
             uint32_t pk[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) {
@@ -170,9 +172,10 @@ removal_corr_sm100_kernel(const __grid_constant__ CorrMaps maps, const CorrParam
                 pk[c] = *reinterpret_cast<uint32_t*>(&b2);
             }
             if (j >= 2) {
-                mbar_wait(p_free + b, ((j - 2) >> 1) & 1);     // D(j-2) has consumed this P buffer
+                if (!pf_ready) mbar_wait(p_free + b, ((j - 2) >> 1) & 1);     // D(j-2) has consumed this P buffer
                 tc_fence_after();
             }
+            s_ready = (j + 1 < nT) ? mbar_test(s_full, (j + 1) & 1) : 0u;
             tmem_st16(tmem + lane_off + COL_P + b * 32 + half * 16, pk);
             tmem_wait_st();
             tc_fence_before();

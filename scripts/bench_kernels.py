@@ -185,6 +185,17 @@ if only in ("corr", "sweep"):
     corr_case(8, 4096, 40, 640)
     corr_case(8, 1024, 80, 100)
 
+if only == "fwd40":
+    for np_ in (2, 3, 4):
+        cfg(0, np_)
+        print(f"--- fwd: {np_}/8 pairs on the polynomial", flush=True)
+        fwd_case("gd_attn_fwd_sm100", 3, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_sm100", 4, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_sm100", 2, 8, 4096, 40)
+        fwd_case("gd_attn_fwd_sm100", 3, 8, 1024, 80)
+        fwd_case("gd_attn_fwd_sm100", 1, 2, 9216, 40)
+    cfg(0, 2)
+
 if only == "rows":
     rows_case(8, 4096, 40, 76)
     rows_case(8, 4096, 40, 410)
