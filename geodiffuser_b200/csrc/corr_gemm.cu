@@ -125,10 +125,6 @@ __global__ void __launch_bounds__(GE_THREADS) gemm_nt_kernel(const GemmParams p)
     }
 }
 
-}  // namespace gd
-
-using namespace gd;
-
 // ---------------------------------------------------------------------------------------------------------------------------
 // Removal-loss gradient of the edit queries, as its own small contraction (round 2b).
 //
@@ -271,6 +267,10 @@ template <int D> static int launch_removal_dq_rows(dim3 grid, cudaStream_t st, c
     GD_CHECK_LAUNCH();
     return GD_OK;
 }
+
+}  // namespace gd
+
+using namespace gd;
 
 extern "C" {
 
