@@ -170,13 +170,16 @@ __global__ void __launch_bounds__(256) loss_reduce_kernel(const LossReduceParams
 // ---- amodal interpolation (depends only on the mask and the grid: built once per resolution per edit) ----------
 // For every pixel the 4 largest inverse grid distances to pixels of the foreground (mask > 0.5), attention_sharing.py:79-83;
 // ties resolved by ascending pixel index.  w[p] = exp(-(1 / max inv) / 5)  (:103)
-__global__ void amodal_knn_kernel(const float* __restrict__ m_edit, int S, int* __restrict__ idx4, float* __restrict__ val4,
-                                  float* __restrict__ w) {
+// One warp per pixel p (round 1: one thread per pixel scanning all N candidates, 1.08 ms at S = 64 on 32 SMs): lane l keeps the top 4 of the
+// candidates q = l, l + 32, ... (ascending q, strict comparison: equal values keep the lower index first), then four rounds of a warp arg-max over
+// the lanes' current heads under the same total order (value descending, index ascending) merge them -- the result is the serial scan's, bit for bit.
+__global__ void __launch_bounds__(256) amodal_knn_kernel(const float* __restrict__ m_edit, int S, int* __restrict__ idx4, float* __restrict__ val4,
+                                                         float* __restrict__ w) {
     const int N = S * S;
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = (int)(((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (p >= N) return;
-    float bv[4] = {-1.f, -1.f, -1.f, -1.f}; int bi[4] = {0, 0, 0, 0};
-    for (int q = 0; q < N; ++q) {
+    float bv[4] = {-1.f, -1.f, -1.f, -1.f}; int bi[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+    for (int q = lane; q < N; q += 32) {
         const float fg = (m_edit[q] > 0.5f) ? 1.f : 0.f;
         const float dist = grid_dist(p, q, S) * 512.f / 2.0f + 100000.f * (1.0f - fg);
         const float inv = 1.0f / (dist + 1e-4f);
@@ -186,9 +189,27 @@ __global__ void amodal_knn_kernel(const float* __restrict__ m_edit, int S, int* 
             bv[pos] = inv; bi[pos] = q;
         }
     }
+    float head_v = bv[0]; int head_i = bi[0];
+    int taken = 0;
+    float first = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { idx4[p * 4 + k] = bi[k]; val4[p * 4 + k] = bv[k]; }
-    w[p] = expf(-(1.0f / bv[0]) / 5.0f);
+    for (int k = 0; k < 4; ++k) {
+        float v = head_v; int i = head_i;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+        if (i == head_i && v == head_v) {            // this lane's head won (indices are unique across lanes): advance it
+            ++taken;
+            head_v = taken == 1 ? bv[1] : taken == 2 ? bv[2] : taken == 3 ? bv[3] : -2.f;
+            head_i = taken == 1 ? bi[1] : taken == 2 ? bi[2] : taken == 3 ? bi[3] : 0x7fffffff;
+        }
+        if (k == 0) first = v;
+        if (lane == 0) { idx4[p * 4 + k] = i; val4[p * 4 + k] = v; }
+    }
+    if (lane == 0) w[p] = expf(-(1.0f / first) / 5.0f);
 }
 
 // u[h,p,c] = fg[p] ? e[h,p,c] : sum_k val[p,k] e[h, idx[p,k], c] / (sum_k val[p,k] + 1e-12)
@@ -302,7 +323,7 @@ int gd_loss_reduce(const float* partials, int n_part, const float* rem_terms, in
 
 int gd_amodal_knn(const float* m_edit, int S, int* idx4, float* val4, float* w, void* stream) {
     GD_CHECK_ARG(m_edit && idx4 && val4 && w && S > 1);
-    amodal_knn_kernel<<<ceil_div((long)S * S, 128), 128, 0, (cudaStream_t)stream>>>(m_edit, S, idx4, val4, w);
+    amodal_knn_kernel<<<ceil_div((long)S * S * 32, 256), 256, 0, (cudaStream_t)stream>>>(m_edit, S, idx4, val4, w);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }

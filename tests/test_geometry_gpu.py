@@ -171,3 +171,36 @@ def test_query_warp_rows_kernel_bit_exact_vs_pixel_kernel_and_oracle(geo, kind, 
     ref = O.splat_composite(nchw[:1].float().cpu().numpy(), idx.cpu().numpy(), d2.cpu().numpy())
     got = G.splat_composite(src, idx, d2, channels_last=True, out_dtype=torch.float32)
     assert relerr(got[:1].permute(0, 2, 1).reshape(1, C, S, S).cpu().numpy(), ref) <= 1e-3   # one fp16 ulp (see make_golden)
+
+
+@pytest.mark.parametrize("S", [64, 96])
+def test_amodal_knn_table_is_the_serial_scan(S):
+    """gd_amodal_knn (one warp per pixel, lane-local top 4 + warp merge) must give the table a serial scan over all candidates gives: the 4 largest
+    inverse grid distances to foreground pixels per pixel, ties by ascending pixel index (attention_sharing.py:79-83).  Checked against torch on the
+    values (sorted) and on the selected distances; the weights w = exp(-(1 / max inv) / 5)."""
+    from geodiffuser_b200._lib import call, ptr, stream
+    from oracle import geodiff_oracle as O
+
+    N = S * S
+    m = torch.zeros(S, S, device="cuda")
+    m[S // 5:S // 2, S // 4:S // 2 + 3] = 1.0
+    m[S - 7, 3] = 1.0
+    m = m.reshape(-1).contiguous()
+    idx = torch.empty(N, 4, device="cuda", dtype=torch.int32)
+    val = torch.empty(N, 4, device="cuda")
+    w = torch.empty(N, device="cuda")
+    call("gd_amodal_knn", ptr(m), S, ptr(idx), ptr(val), ptr(w), stream())
+    dgrid = O.distance_grid(S).cuda()                                                # (1, N, N)
+    fg = (m > 0.5).float()
+    inv = 1.0 / (dgrid[0] * 512 / 2.0 + 100000 * (1.0 - fg)[None, :] + 1e-4)
+    ref = torch.topk(inv, k=4, dim=-1, largest=True, sorted=True)
+    # (the kernel forms the grid coordinates as (2i+1)/S - 1, torch's affine_grid as a linspace: distances agree to ~1e-7 absolute, i.e. ~1e-5
+    #  relative between neighbouring pixels; neighbouring CANDIDATES differ by per cent)
+    assert torch.allclose(val, ref.values, rtol=1e-4, atol=0)
+    picked = torch.gather(inv, 1, idx.long())
+    assert torch.allclose(picked, ref.values, rtol=1e-4, atol=0)                    # the indices point at those candidates
+    assert (fg[idx.long()] == 1).all() and (idx[:, 0] != idx[:, 1]).all()
+    # equal distances: lower pixel index first
+    same = val[:, :-1] == val[:, 1:]
+    assert (idx[:, :-1][same] < idx[:, 1:][same]).all()
+    assert torch.allclose(w, torch.exp(-(1 / ref.values[:, 0]) / 5), rtol=1e-4)
