@@ -60,7 +60,9 @@ class EditWorkers:
         self.device = dev if dev.index is not None else torch.device("cuda", torch.cuda.current_device())
         self.models = [model] + [replicate_model(model) for _ in range(max(1, lanes) - 1)]
         self.streams = [torch.cuda.Stream(device=self.device) for _ in self.models]
-        self._jobs = [queue.Queue() for _ in self.models]
+        self._jobs = queue.Queue()          # ONE queue for all lanes: a lane takes the next request when it is free (requests differ in cost:
+                                            # a 768^2 edit is ~2.3 x a 512^2 one, and a static deal leaves lanes idle at the end of a batch)
+        self._own = [queue.Queue() for _ in self.models]      # requests pinned to one lane (warm-up: map_every_lane)
         self._done = queue.Queue()
         self._threads = [threading.Thread(target=self._lane, args=(w,), daemon=True) for w in range(len(self.models))]
         for t in self._threads:
@@ -77,8 +79,16 @@ class EditWorkers:
             (a @ a).float() @ torch.ones(8, 8, device=self.device)
             torch.nn.functional.conv2d(a.reshape(1, 1, 8, 8), torch.ones(1, 1, 3, 3, device=self.device, dtype=torch.bfloat16), padding=1)
             self.streams[w].synchronize()
+        import queue
+
         while True:
-            job = self._jobs[w].get()
+            try:
+                job = self._own[w].get_nowait()
+            except queue.Empty:
+                try:
+                    job = self._jobs.get(timeout=0.002)
+                except queue.Empty:
+                    continue
             if job is None:
                 return
             fn, item, idx, after = job
@@ -96,11 +106,11 @@ class EditWorkers:
                 self._done.put((idx, None, e))
 
     def map(self, fn, items):
-        """results[i] = fn(lane's model, items[i]); returns once every lane has queued its work, with the calling stream waiting for all lanes"""
-        n = len(self.models)
+        """results[i] = fn(a lane's model, items[i]), in the order of `items`; requests are started in that order, each by the first lane that is
+        free.  Returns once every request has been queued on its lane's stream, with the calling stream waiting for all lanes."""
         cur = torch.cuda.current_stream(self.device)
         for i, item in enumerate(items):
-            self._jobs[i % n].put((fn, item, i, cur))
+            self._jobs.put((fn, item, i, cur))
         results, error = [None] * len(items), None
         for _ in items:
             idx, res, err = self._done.get()
@@ -111,8 +121,27 @@ class EditWorkers:
             raise error
         return results
 
+    def map_every_lane(self, fn, items):
+        """fn(lane's model, item) for every item on EVERY lane (warm-up: graphs, per-thread plan caches); -> results of lane 0"""
+        n = len(self.models)
+        cur = torch.cuda.current_stream(self.device)
+        for w in range(n):
+            for i, item in enumerate(items):
+                self._own[w].put((fn, item, (w, i), cur))
+        results, error = [None] * len(items), None
+        for _ in range(n * len(items)):
+            (w, i), res, err = self._done.get()
+            if w == 0:
+                results[i] = res
+            error = err if err is not None and error is None else error
+        for s in self.streams:
+            cur.wait_stream(s)
+        if error is not None:
+            raise error
+        return results
+
     def close(self):
-        for q in self._jobs:
+        for q in self._own:
             q.put(None)
 
 
