@@ -95,3 +95,16 @@ def test_stride_and_shape_validation_happens_before_any_launch():
     assert rc == 1                                            # C % 8 != 0
     rc = L.gd_masked_histogram_match(p, p, p, p, 0, 3, p, p, p, None)
     assert rc == 1                                            # npix == 0
+    # removal rows of dQ: head dims / key counts the kernel was not built for, unaligned K slabs, odd leading dimensions
+    rc = L.gd_removal_dq_rows(p, p, p, None, p, 1, 4, 1024, 1024, 64, ctypes.c_float(1.0), 1024, None, 0, None)
+    assert rc == 3 and b"d in {40, 80}" in L.gd_last_error()
+    rc = L.gd_removal_dq_rows(p, p, p, None, p, 1, 4, 1000, 1000, 40, ctypes.c_float(1.0), 1000, None, 0, None)
+    assert rc == 3
+    bad4 = (ctypes.c_long * 4)(40, 12, 40, 8)
+    rc = L.gd_removal_dq_rows(p, p, p, None, p, 1, 4, 1024, 1024, 40, ctypes.c_float(1.0), 1024, bad4, 0, None)
+    assert rc == 1 and b"16-byte" in L.gd_last_error()
+    rc = L.gd_removal_weighted_rows(p, p, p, 1, 4, 1024, 1023, p, None)
+    assert rc == 1                                            # ld < Nk
+    rc = L.gd_attn_sm100_config(2, 96)
+    assert rc == 1                                            # keys per step: 0 / 64 / 128 only
+    assert L.gd_attn_sm100_config(2, 0) == 0

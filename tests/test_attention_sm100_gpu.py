@@ -199,3 +199,73 @@ def test_forward_reference_moves_inside_a_tile(d, pattern):
     assert torch.isfinite(O[0]).all() and torch.isfinite(LSE[0]).all()
     assert relerr(O[0].cpu().numpy(), ref.cpu().numpy()) <= 1e-2
     assert relerr(LSE[0].cpu().numpy(), torch.logsumexp(s, -1).cpu().numpy()) <= 1e-3
+
+
+@pytest.mark.parametrize("bnk", [64, 128])
+@pytest.mark.parametrize("N,d,H,G", [(1024, 40, 8, 3), (1024, 80, 4, 2)])
+@pytest.mark.timeout(120)
+def test_sm100_forward_both_step_sizes(bnk, N, d, H, G):
+    """gd_attn_sm100_config key 2: 64- and 128-key steps are the same computation (the default picks 128 at head_dim 40, 64 at head_dim 80; the
+    other two instances exist for A/B measurements and must stay correct): head_dim 40 at 64 keys runs on two TMEM allocations, three CTAs per SM."""
+    from geodiffuser_b200._lib import call
+
+    g = torch.Generator(device="cuda").manual_seed(N + d + bnk)
+    mk = lambda: (torch.randn(H, N, d, device="cuda", generator=g) * 1.5).bfloat16()
+    qs = [mk() for _ in range(G)]
+    k, v = mk(), mk()
+    scale = d ** -0.5
+    try:
+        call("gd_attn_sm100_config", 2, bnk)
+        O, L = _run("gd_attn_fwd_sm100", qs, [k] * G, [v] * G, scale)
+    finally:
+        call("gd_attn_sm100_config", 2, 0)
+    for i in range(G):
+        s = torch.einsum("hnd,hkd->hnk", qs[i].float(), k.float()) * scale
+        ref = torch.softmax(s, -1) @ v.float()
+        assert relerr(O[i].cpu().numpy(), ref.cpu().numpy()) <= 1e-2, i
+        assert relerr(L[i].cpu().numpy(), torch.logsumexp(s, -1).cpu().numpy()) <= 1e-3, i
+
+
+@pytest.mark.parametrize("N,d,H,M,proj,dq_dtype", [(4096, 40, 8, 76, False, torch.float32), (1024, 80, 8, 18, True, torch.bfloat16),
+                                                   (1024, 40, 2, 37, True, torch.float32), (2304, 80, 2, 300, False, torch.bfloat16)])
+@pytest.mark.timeout(120)
+def test_removal_dq_rows_is_the_weighted_contraction(N, d, H, M, proj, dq_dtype):
+    """gd_removal_weighted_rows + gd_removal_dq_rows: dq[h, rows[m], :] += gscale * scale * sum_k (A_e[m,k] (g_bg P2[m,k] + g_in P2[M+m,k])) K[h,k,:]
+    -- the removal term of dQ (attention_processors.py:262-280 through autograd in the reference) -- against fp32 on the same bf16 operands, with
+    contiguous slabs and with the projection layout (B, N, H*d) the processors hand over, accumulating into fp32 and bf16 gradients."""
+    from geodiffuser_b200._lib import call, ptr, stream, host_longs
+
+    g = torch.Generator(device="cuda").manual_seed(N + d + M)
+    ld = (N + 7) // 8 * 8
+    a_e = (torch.rand(H, M, ld, device="cuda", generator=g) * 0.02).bfloat16()
+    p2 = (torch.rand(H, 2 * M, ld, device="cuda", generator=g) * 0.02).bfloat16()
+    g2 = torch.randn(H * M, 2, device="cuda", generator=g)
+    rows = torch.randperm(N, device="cuda", generator=g)[:M].sort().values.int()
+    gs = torch.full((1,), 0.7, device="cuda")
+    scale = d ** -0.5
+    if proj:
+        kfull = (torch.randn(N, H * d, device="cuda", generator=g) * 1.5).bfloat16()
+        k = kfull.reshape(N, H, d).permute(1, 0, 2)                                   # (H, N, d) view of the projection layout
+        dqfull = (torch.randn(N, H * d, device="cuda", generator=g) * 0.01).to(dq_dtype)
+        dq = dqfull.reshape(N, H, d).permute(1, 0, 2)
+        strides = host_longs([H * d, d, H * d, d])
+        kbase, dqbase = kfull, dqfull
+    else:
+        k = (torch.randn(H, N, d, device="cuda", generator=g) * 1.5).bfloat16()
+        dq = (torch.randn(H, N, d, device="cuda", generator=g) * 0.01).to(dq_dtype)
+        strides, kbase, dqbase = None, k, dq
+    before = dq.float().clone()
+    w = torch.empty(H, M, ld, device="cuda", dtype=torch.bfloat16)
+    call("gd_removal_weighted_rows", ptr(a_e), ptr(p2), ptr(g2), H, M, N, ld, ptr(w), stream())
+    call("gd_removal_dq_rows", ptr(w), ptr(kbase), ptr(rows), ptr(gs), ptr(dqbase), H, M, N, N, d, float(scale), ld, strides, int(dq_dtype == torch.bfloat16), stream())
+    torch.cuda.synchronize()
+    gg = g2.reshape(H, M, 2)
+    wr = a_e.float() * (gg[..., :1] * p2[:, :M].float() + gg[..., 1:] * p2[:, M:].float())
+    assert relerr(w[:, :, :N].float().cpu().numpy(), wr[:, :, :N].cpu().numpy()) <= 1e-2          # bf16 rounding of W
+    add = torch.einsum("hmk,hkd->hmd", wr[:, :, :N], k.float()) * scale * 0.7
+    got = dq.float() - before
+    tol = 1e-2 if dq_dtype == torch.float32 else 5e-2                                 # (bf16 accumulation rounds the sum to 8 bits)
+    assert relerr(got[:, rows.long()].cpu().numpy(), add.cpu().numpy()) <= tol
+    untouched = torch.ones(N, dtype=torch.bool, device="cuda")
+    untouched[rows.long()] = False
+    assert torch.equal(got[:, untouched], torch.zeros_like(got[:, untouched]))         # rows outside the inpaint set are not written
