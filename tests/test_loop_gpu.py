@@ -133,12 +133,12 @@ def test_whole_network_gradient_vs_oracle(tiny_model, kind):
     assert abs(float(c.loss) - float(oc.loss)) <= 2e-2 * abs(float(oc.loss))
     e_lat = rel(g_l[-1].cpu(), go_l[-1])
     print(f"{kind}: loss {float(c.loss):.4f} / {float(oc.loss):.4f}, d loss/d latent relerr {e_lat:.2e}")
-    assert e_lat <= 3e-2          # measured 1.8e-2 (translate2d), 1.9e-2 (remove)
+    assert e_lat <= 2e-2          # the BASELINE gate; measured 1.6e-2 (translate2d), 1.9e-2 (remove)
     assert float(g_l[0].abs().max()) == 0.0 and float(go_l[0].abs().max()) == 0.0   # the reference sample never receives a gradient
     if go_c is not None and float(go_c[-1].abs().max()) > 0:
         e_ctx = rel(g_c[-1].cpu(), go_c[-1])
         print(f"{kind}: d loss/d context relerr {e_ctx:.2e}")
-        assert e_ctx <= 3e-2      # measured 1.1e-2
+        assert e_ctx <= 2e-2      # measured 1.1e-2
     else:
         assert g_c is None or float(g_c.abs().max()) == 0.0  # the remover's cross layers attend detached base keys: no context gradient
 
