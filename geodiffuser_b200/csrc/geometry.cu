@@ -44,45 +44,28 @@ __global__ void pixel2cam_kernel(const float* __restrict__ depth, int H, int W, 
     for (int r = 0; r < 3; ++r) cam[r * hw + p] = __fmul_rn(dot3_fma(Kinv.m + 3 * r, (float)u, (float)v, 1.0f), d);
 }
 
-// canonical centroid: double accumulation left-to-right inside a row, then the row partials top-to-bottom.  out4 = {mean_x, mean_y, mean_z, count}
-// The order is part of the bit-exactness contract (the oracle adds in the same order), so one thread still owns a row's additions -- but the row's
-// pixels reach it through shared memory: the block walks the image 32 rows at a time, loads 32 x 32 tiles coalesced (one warp per row segment) and
-// thread r of warp 0 walks row r of the tile.  Round 1 let every thread read its own row from global memory (stride W between neighbouring lanes):
-// 197 us at 512^2 for 4 MB.
-__global__ void __launch_bounds__(1024) centroid_kernel(const float* __restrict__ cam, const float* __restrict__ mask, int H, int W,
-                                                        float* __restrict__ out4) {
+// canonical centroid: double accumulation left-to-right inside a row (one thread per row), then the
+// row partials top-to-bottom (thread 0).  out4 = {mean_x, mean_y, mean_z, count}
+// (197 us at 512^2: every thread walks its own row, stride W between neighbouring lanes.  Two single-block forms that stage the rows through shared
+//  memory -- 32 rows at a time, and all rows in 16-column strips -- kept the order but measured 426 and 253 us: one SM cannot pull 4 MB faster, and a
+//  multi-block form needs a partials workspace the entry point does not have.  Once per edit, 0.04 % of its time: left as it is.)
+__global__ void centroid_kernel(const float* __restrict__ cam, const float* __restrict__ mask, int H, int W,
+                                float* __restrict__ out4) {
     extern __shared__ double part[];  // H * 4
-    __shared__ float tile[4][32][33];
     const long hw = (long)H * W;
-    const int ty = threadIdx.x >> 5, tx = threadIdx.x & 31;      // ty: row of the tile this warp loads; tx: column
-    for (int r0 = 0; r0 < H; r0 += 32) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, c = 0.0;             // thread (ty == 0, tx = r) accumulates row r0 + tx
-        for (int u0 = 0; u0 < W; u0 += 32) {
-            const int v = r0 + ty, u = u0 + tx;
-            const bool ok = v < H && u < W;
+    const int v = threadIdx.x;
+    if (v < H) {
+        double r0 = 0.0, r1 = 0.0, r2 = 0.0, c = 0.0;
+        for (int u = 0; u < W; ++u) {
             const long p = (long)v * W + u;
-            tile[0][ty][tx] = ok ? mask[p] : 0.f;
-            tile[1][ty][tx] = ok ? cam[p] : 0.f;
-            tile[2][ty][tx] = ok ? cam[hw + p] : 0.f;
-            tile[3][ty][tx] = ok ? cam[2 * hw + p] : 0.f;
-            __syncthreads();
-            if (ty == 0) {
-#pragma unroll 8
-                for (int k = 0; k < 32; ++k) {
-                    if (tile[0][tx][k] >= 0.5f) {
-                        a0 += (double)tile[1][tx][k];
-                        a1 += (double)tile[2][tx][k];
-                        a2 += (double)tile[3][tx][k];
-                        c += 1.0;
-                    }
-                }
+            if (mask[p] >= 0.5f) {
+                r0 += (double)cam[p];
+                r1 += (double)cam[hw + p];
+                r2 += (double)cam[2 * hw + p];
+                c += 1.0;
             }
-            __syncthreads();
         }
-        if (ty == 0 && r0 + tx < H) {
-            double* o = part + 4 * (r0 + tx);
-            o[0] = a0; o[1] = a1; o[2] = a2; o[3] = c;
-        }
+        part[4 * v + 0] = r0; part[4 * v + 1] = r1; part[4 * v + 2] = r2; part[4 * v + 3] = c;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -505,7 +488,8 @@ int gd_corr_pixel2cam(const float* depth, const float* mask, int H, int W, const
     const long hw = (long)H * W;
     pixel2cam_kernel<<<ceil_div(hw, 256), 256, 0, st>>>(depth, H, W, Ki, cam);
     GD_CHECK_LAUNCH();
-    centroid_kernel<<<1, 1024, (size_t)H * 4 * sizeof(double), st>>>(cam, mask, H, W, centroid4);
+    const int threads = ((H + 31) / 32) * 32;
+    centroid_kernel<<<1, threads, (size_t)H * 4 * sizeof(double), st>>>(cam, mask, H, W, centroid4);
     GD_CHECK_LAUNCH();
     return GD_OK;
 }
