@@ -370,8 +370,7 @@ def run_mixed64(args, world, rank, dev, workers, barrier):
     warm = [make(1000 + j, k) for k in ("translate2d", "rotate3d", "remove", "rotate3d@768") for j in range(2)]
     workers.map_every_lane(api, warm)
     # longest first: a 768^2 edit costs ~2.3 x a 512^2 one, and the lanes of a rank take requests as they become free (runner.EditWorkers)
-    order = sorted(range(len(reqs)), key=lambda i: (0 if kinds[mine[i]].endswith("@768") else 1, i))
-    reqs = [reqs[i] for i in order]
+    reqs = [reqs[i] for i in runner.longest_first([2.3 if kinds[m].endswith("@768") else 1.0 for m in mine])]
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

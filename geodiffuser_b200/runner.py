@@ -12,6 +12,12 @@ def shard_round_robin(n_requests, rank, world_size):
     return list(range(rank, n_requests, world_size))
 
 
+def longest_first(costs):
+    """order in which a rank starts its requests: descending cost, ties in arrival order (its lanes take requests as they become free, so the
+    expensive ones -- a 768^2 edit is ~2.3 x a 512^2 one -- must not be the last to start)"""
+    return sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+
+
 def reduce_throughput(n_done, seconds, device=None):
     """(total edits over all ranks, max seconds over ranks, edits/sec).  Works with nccl (GPU tensors) and gloo (CPU tensors)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:

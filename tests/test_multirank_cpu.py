@@ -45,3 +45,14 @@ def test_round_robin_sharding_and_throughput_reduce():
     for _, _, n, t, thr, gathered in res:
         assert n == 7.0 and t == 2.0 and abs(thr - 3.5) < 1e-9
         assert sorted(sum(gathered, [])) == list(range(7))          # every request served exactly once, no overlap
+
+
+def test_requests_of_a_rank_start_longest_first():
+    from geodiffuser_b200 import runner
+
+    assert runner.longest_first([1.0, 2.3, 1.0, 2.3, 1.0]) == [1, 3, 0, 2, 4]
+    assert runner.longest_first([]) == []
+    # every request of the shard is started exactly once, whatever the costs
+    shard = runner.shard_round_robin(64, 3, 8)
+    order = runner.longest_first([2.3 if i % 4 == 3 else 1.0 for i in shard])
+    assert sorted(order) == list(range(len(shard)))
