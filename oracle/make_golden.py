@@ -309,7 +309,10 @@ def product_shape_cases(R, geos=None):
 def config3_case(R):
     """BASELINE.json configs[3]: a 768 x 768 image -> 96^2 latent, N = 9216 tokens in the first self-attention level, where the amodal term
     is active as well (N > 32^2, attention_processors.py:596-597).  H = 2 heads keep the reference's materialised (H, N, N) maps in memory."""
-    attention_case(R, "edit_self_S96_H2d40_opt_768", geometry_only(R, "rotate3d", size=768), "edit", 96, 2, 40, False, False, 206, subsample=32)
+    geo768 = geometry_only(R, "rotate3d", size=768)
+    attention_case(R, "edit_self_S96_H2d40_opt_768", geo768, "edit", 96, 2, 40, False, False, 206, subsample=32)
+    # ... and its second loss level: S = 48, N = 2304, head_dim 80, all 8 heads; still above the 32^2 gate of the amodal term
+    attention_case(R, "edit_self_S48_H8d80_opt_768", geo768, "edit", 48, 8, 80, False, False, 207, subsample=12)
 
 
 def geometry_only(R, cfg, size=512):

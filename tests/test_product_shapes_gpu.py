@@ -39,6 +39,8 @@ CASES = [  # name, geometry, kind, S, H, d, use_cfg, seed        (oracle/make_go
     # BASELINE.json configs[3]: a 768 x 768 image -> first self-attention level S = 96, N = 9216 (H = 2: the reference's materialised maps);
     # the amodal term is active here (N > 32^2)
     ("edit_self_S96_H2d40_opt_768", "rotate3d", "edit", 96, 2, 40, False, 206),
+    # ... and the second loss level of the 768^2 edit: S = 48, N = 2304, head_dim 80, all 8 heads (amodal term still active: N > 32^2)
+    ("edit_self_S48_H8d80_opt_768", "rotate3d", "edit", 48, 8, 80, False, 207),
 ]
 
 
