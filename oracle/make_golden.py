@@ -194,7 +194,7 @@ def attention_case(R, name, geo, kind, S, H, d, is_cross, use_cfg, seed, cur_ste
         rec["dq_absmax"] = np.float64(np.abs(gq.numpy()).max())
         if gk is not None:
             check("dk", g2k.numpy(), gk.numpy(), 1e-4)
-            if not subsample:       # (self layers at the product shapes: dK belongs to the detached base sample, not stored)
+            if not subsample or is_cross:       # (self layers at the product shapes: dK belongs to the detached base sample, not stored)
                 rec["dk"] = gk.numpy()
                 if lk is not None:
                     rec["dk_loss"] = lk.numpy()
@@ -304,6 +304,15 @@ def product_shape_cases(R, geos=None):
     attention_case(R, "edit_self_S32_H8d80_opt", geos["translate2d"], "edit", 32, 8, 80, False, False, 204, subsample=8)
     attention_case(R, "remove_self_S32_H8d80_opt", geos["remove"], "remove", 32, 8, 80, False, False, 205, subsample=8)
     config3_case(R)
+    cross_cases(R, geos)
+
+
+def cross_cases(R, geos=None):
+    """cross-attention layers (77 text keys) at the UNet's real shapes: served by the mma.sync kernels (forward, dQ, dK with the split query walk)"""
+    if geos is None:
+        geos = {name: geometry_only(R, name) for name in ("translate2d", "rotate3d")}
+    attention_case(R, "edit_cross_S64_H8d40_opt", geos["rotate3d"], "edit", 64, 8, 40, True, False, 208, subsample=16)
+    attention_case(R, "edit_cross_S32_H8d80_opt", geos["translate2d"], "edit", 32, 8, 80, True, False, 209, subsample=8)
 
 
 def config3_case(R):
@@ -337,6 +346,9 @@ if __name__ == "__main__":
     if "--config3" in sys.argv:
         torch.set_grad_enabled(True)
         sys.exit(config3_case(load_reference()))
+    if "--cross" in sys.argv:
+        torch.set_grad_enabled(True)
+        sys.exit(cross_cases(load_reference()))
     if "--product-shapes" in sys.argv:     # only the H = 8 cases (the rest of the golden set is left untouched)
         torch.set_grad_enabled(True)
         sys.exit(product_shape_cases(load_reference()))

@@ -126,3 +126,60 @@ def test_controller_at_product_shapes(case, layout):
     assert e_up <= TOL
     assert e_rem <= TOL
     assert share_el >= 0.99 and share_row >= 0.98, (e_max, share_el, share_row)
+
+
+CROSS_CASES = [  # name, geometry, S, H, d, seed        (oracle/make_golden.py:cross_cases)
+    ("edit_cross_S64_H8d40_opt", "rotate3d", 64, 8, 40, 208),
+    ("edit_cross_S32_H8d80_opt", "translate2d", 32, 8, 80, 209),
+]
+
+
+@pytest.mark.parametrize("layout", ["proj", "heads"])
+@pytest.mark.parametrize("case", CROSS_CASES, ids=[c[0] for c in CROSS_CASES])
+def test_cross_controller_at_product_shapes(case, layout):
+    """The cross-attention layers (77 text keys) of the same UNet levels, against the reference's AttentionGeometryEdit.replace_cross_attention
+    (attention_processors.py:384-508): served by the mma.sync kernels -- forward, dQ, and dK of the edit sample's keys with the query walk split over
+    the grid.  Smooth parts (output, loss terms, the upstream gradient through the output for dQ and dK) at the 2e-2 max-norm gate; the loss
+    gradient by the share of agreeing elements (sign / arg-max decisions, see the module docstring) with its max-norm printed."""
+    from geodiffuser_b200 import functional as Fn
+
+    name, gname, S, H, d, seed = case
+    z = np.load(os.path.join(GOLDEN, f"attn_{name}.npz"))
+    rows = torch.from_numpy(z["rows"].astype(np.int64)).cuda()
+    geo = geometry_for(gname, 512)
+    c = make_controller("edit", geo, 0, False)
+    B = 2
+    q, k, v = (torch.from_numpy(a).cuda() for a in synth.qkv(seed, B, H, S * S, 77, d))
+    to_proj = lambda t: t.reshape(B, H, t.shape[1], d).permute(0, 2, 1, 3).reshape(B, t.shape[1], H * d).contiguous()
+    to_heads = lambda t: t.reshape(B, t.shape[1], H, d).permute(0, 2, 1, 3).reshape(B * H, t.shape[1], d)
+    if layout == "proj":
+        q, k, v = to_proj(q), to_proj(k), to_proj(v)
+    q, k, v = (t.requires_grad_(True) for t in (q, k, v))
+    args = (Fn.ProjView(q, H), Fn.ProjView(k, H), Fn.ProjView(v, H)) if layout == "proj" else (q, k, v)
+    with torch.enable_grad():
+        out = c(*args, True, "down", transform_coords=geo["coords"], scale=d ** -0.5, mask=None)
+    out_h = (to_heads(out) if layout == "proj" else out).detach().float()
+    e_out = relerr(out_h[:, rows].cpu().numpy(), z["out"])
+    assert e_out <= TOL
+    loss = c.loss
+    assert abs(float(loss.detach()) - float(z["loss"])) <= TOL * abs(float(z["loss"])), (float(loss.detach()), float(z["loss"]))
+    for key, val in c.loss_log_dict["cross"].items():
+        ref = float(z["term_" + key])
+        assert abs(float(val) - ref) <= TOL * max(abs(ref), 0.05), (key, float(val), ref)
+    glq, glk = torch.autograd.grad(loss, [q, k], retain_graph=True)
+    guq, guk = torch.autograd.grad(0.37 * out.float().sum(), [q, k])
+    if layout == "proj":
+        glq, glk, guq, guk = (to_heads(t) for t in (glq, glk, guq, guk))
+    assert float(glq[:H].abs().max()) == 0.0 and float(guq[:H].abs().max()) == 0.0          # base sample: detached
+    pick = lambda g: g[H:, rows].float().cpu().numpy()
+    up_q = (z["dq"] - z["dq_loss"])[H:]
+    e_upq, _, _ = stats(pick(guq), up_q, float(np.abs(up_q).max()))
+    up_k = (z["dk"] - z["dk_loss"])[H:]
+    e_upk, _, _ = stats(guk[H:].float().cpu().numpy(), up_k, float(np.abs(up_k).max()))
+    e_q, share_q, rows_q = stats(pick(glq), z["dq_loss"][H:], float(z["dq_loss_absmax"]))
+    e_k, share_k, _ = stats(glk[H:].float().cpu().numpy(), z["dk_loss"][H:], float(np.abs(z["dk_loss"]).max()))
+    print(f"{name} [{layout}]: out {e_out:.2e}; upstream-only dq {e_upq:.2e}, dk {e_upk:.2e}; loss gradient: dq max-norm {e_q:.2e}, elements within 2e-2 "
+          f"{100 * share_q:.3f} %, rows {100 * rows_q:.2f} %; dk max-norm {e_k:.2e}, elements within 2e-2 {100 * share_k:.2f} %")
+    assert e_upq <= TOL and e_upk <= TOL
+    assert share_q >= 0.99 and rows_q >= 0.98, (e_q, share_q, rows_q)
+    assert share_k >= 0.95, (e_k, share_k)
