@@ -43,6 +43,30 @@ def test_oracle_attention_layer_vs_golden():
     assert relerr(res["out"].numpy(), z["out"]) <= 2e-5
 
 
+def test_oracle_cross_layer_at_product_shape_vs_golden():
+    """edit_cross_S32_H8d80_opt (H = 8, head_dim 80, N = 1024 x 77 keys: cheap on the CPU): the oracle's layer with losses and its gradients against
+    the golden the REFERENCE's AttentionGeometryEdit produced (oracle/make_golden.py:cross_cases) -- output, loss, every logged term, dQ and dK"""
+    z = np.load(os.path.join(GOLDEN, "attn_edit_cross_S32_H8d80_opt.npz"))
+    S, H, d = 32, 8, 80
+    image, depth, mask, T = synth.edit_inputs("translate2d")
+    g = O.corr_build(depth.copy(), mask.copy(), T)
+    amodal = O.erode3(O.mesh_mask(g["coords"], g["mask"]))
+    idx512, _, d2 = O.splat_index(g["coords"][None])
+    mnw = O.binarize(O.splat_composite(mask.astype(np.float32)[None, None], idx512, d2))[0, 0]
+    masks = O.build_masks(mask.astype(np.float32), mnw, amodal, S)
+    q, k, v = (torch.from_numpy(a).requires_grad_(True) for a in synth.qkv(209, 2, H, S * S, 77, d))
+    with torch.enable_grad():
+        res = O.edit_layer(q, k, v, True, d ** -0.5, H, (0, 1), (1, 2), masks, O.resize_coords(g["coords"], S), False, True)
+        gq, gk = torch.autograd.grad(res["loss"] + 0.37 * res["out"].sum(), [q, k])
+    rows = z["rows"]
+    assert relerr(res["out"].detach().numpy()[:, rows], z["out"]) <= 2e-5
+    assert abs(float(res["loss"]) - float(z["loss"])) <= 2e-5 * abs(float(z["loss"]))
+    for key in ("sim", "movement", "removal", "smoothness"):
+        assert abs(float(res["terms"][key]) - float(z["term_" + key])) <= 5e-4 * max(abs(float(z["term_" + key])), 1e-6), key
+    assert relerr(gq.numpy()[:, rows], z["dq"]) <= 1e-4
+    assert relerr(gk.numpy(), z["dk"]) <= 1e-4
+
+
 def test_oracle_elementwise_vs_golden():
     z = np.load(os.path.join(GOLDEN, "elementwise.npz"))
     lat, ctx = torch.from_numpy(z["lat"]), torch.from_numpy(z["ctx"])
